@@ -1,0 +1,665 @@
+// C ABI (include/floodsr_b200.h) and the Engine that executes the lowered plan.
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "fsr_engine.cuh"
+
+namespace fsr {
+
+thread_local LaunchCounter* g_launch_counter = nullptr;
+static thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------------
+
+Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t weights_count, int device, int precision)
+    : device_(device), precision_(precision) {
+  FSR_REQUIRE(plan && plan_bytes >= sizeof(fsr_plan_header), "plan is empty");
+  memcpy(&hdr_, plan, sizeof(hdr_));
+  FSR_REQUIRE(hdr_.magic == FSR_PLAN_MAGIC && hdr_.version == FSR_PLAN_VERSION, "plan magic/version mismatch");
+  FSR_REQUIRE(hdr_.n_tensors >= 3 && hdr_.n_ops >= 1, "plan has no layers");
+  size_t need = sizeof(hdr_) + (size_t)hdr_.n_tensors * sizeof(fsr_tensor_desc) + (size_t)hdr_.n_ops * sizeof(fsr_op);
+  FSR_REQUIRE(plan_bytes == need, "plan size does not match its header");
+  const char* p = (const char*)plan + sizeof(hdr_);
+  tensors_.resize(hdr_.n_tensors);
+  memcpy(tensors_.data(), p, tensors_.size() * sizeof(fsr_tensor_desc));
+  p += tensors_.size() * sizeof(fsr_tensor_desc);
+  ops_.resize(hdr_.n_ops);
+  memcpy(ops_.data(), p, ops_.size() * sizeof(fsr_op));
+  FSR_REQUIRE(hdr_.lr_tile > 0 && hdr_.hr_tile == hdr_.lr_tile * hdr_.scale, "inconsistent tile geometry");
+  FSR_REQUIRE(hdr_.hr_tile % 64 == 0, "hr tile must be a multiple of 64");
+  FSR_REQUIRE(hdr_.out_tensor >= 2 && hdr_.out_tensor < hdr_.n_tensors, "bad output tensor");
+  FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_BF16, "unknown precision mode");
+
+  const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
+  big_.assign(tensors_.size(), 0);
+  for (size_t i = 0; i < tensors_.size(); ++i) {
+    const auto& t = tensors_[i];
+    FSR_REQUIRE(t.h > 0 && t.w > 0 && t.c > 0, "bad tensor shape in plan");
+    big_[i] = ((size_t)t.h * t.w * t.c > hr_px) ? 1 : 0;
+  }
+  auto tensor_ok = [&](int id, bool allow_none) { return (allow_none && id == -1) || (id >= 0 && id < hdr_.n_tensors); };
+  std::vector<int> producer(tensors_.size(), -1);
+  op_hr_.assign(ops_.size(), 0);
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    const fsr_op& op = ops_[i];
+    FSR_REQUIRE(op.kind >= FSR_OP_CONV && op.kind <= FSR_OP_HEAD, "unknown op kind in plan");
+    FSR_REQUIRE(tensor_ok(op.src0, false) && tensor_ok(op.src1, true) && tensor_ok(op.res, true) && tensor_ok(op.dst, false),
+                "op references a tensor outside the plan");
+    auto off_ok = [&](int off) { return off == -1 || (off >= 0 && (size_t)off < weights_count); };
+    FSR_REQUIRE(off_ok(op.w_off) && off_ok(op.b_off) && off_ok(op.w2_off) && off_ok(op.b2_off), "weight offset outside blob");
+    bool hr = big_[op.dst] || big_[op.src0] || (op.src1 >= 0 && big_[op.src1]) || (op.res >= 0 && big_[op.res]);
+    if (op.kind == FSR_OP_HEAD) hr = true;
+    op_hr_[i] = hr ? 1 : 0;
+    if (!hr) {
+      for (int s : {op.src0, op.src1, op.res})
+        if (s >= 0 && producer[s] >= 0 && op_hr_[producer[s]])
+          throw Error(FSR_E_UNSUPPORTED, "plan has a low-resolution layer that consumes a high-resolution feature map");
+    }
+    producer[op.dst] = (int)i;
+  }
+
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    throw Error(FSR_E_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+  FSR_REQUIRE(device >= 0 && device < n_dev, "device index out of range");
+  set_device();
+  d_weights_.ensure(std::max<size_t>(weights_count, 1) * sizeof(float));
+  if (weights_count) FSR_CUDA(cudaMemcpy(d_weights_.p, weights, weights_count * sizeof(float), cudaMemcpyHostToDevice));
+  d_flags_.ensure(sizeof(unsigned));
+  FSR_CUDA(cudaMemset(d_flags_.p, 0, sizeof(unsigned)));
+  tbuf_.resize(tensors_.size());
+  tbase_.assign(tensors_.size(), nullptr);
+  if (precision_ == FSR_PREC_BF16) throw Error(FSR_E_UNSUPPORTED, "bf16 tensor-core backend is not built into this library yet");
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  for (auto& b : tbuf_) b.release();
+  for (DeviceBuf* b : {&d_weights_, &d_flags_, &d_headmid_, &d_dem_norm_, &d_depth_norm_, &d_pred_norm_, &d_tiles, &d_stats,
+                       &d_in_depth, &d_in_dem, &d_out, &d_tmp_a, &d_tmp_b})
+    b->release();
+  win.release();
+}
+
+int64_t Engine::macs_per_tile() const {
+  int64_t total = 0;
+  for (const fsr_op& op : ops_) {
+    const auto& d = tensors_[op.dst];
+    if (op.kind == FSR_OP_CONV || op.kind == FSR_OP_HEAD) {
+      int cin = tensors_[op.src0].c + (op.src1 >= 0 ? tensors_[op.src1].c : 0);
+      total += (int64_t)d.h * d.w * op.k * op.k * cin * op.cout;
+      if (op.kind == FSR_OP_HEAD) total += (int64_t)d.h * d.w * op.cout;
+    } else if (op.kind == FSR_OP_CONVT) {
+      total += (int64_t)d.h * d.w * tensors_[op.src0].c * op.cout;
+    }
+  }
+  return total;
+}
+
+void Engine::ensure_arena(int n_tiles) {
+  if (n_tiles <= cap_tiles_) return;
+  const int cap = std::max(n_tiles, chunk_tiles_);
+  size_t headmid = 0;
+  for (size_t i = 0; i < tensors_.size(); ++i) {
+    if ((int)i == 0 || (int)i == 1 || (int)i == hdr_.out_tensor) continue;  // alias caller buffers
+    const auto& t = tensors_[i];
+    size_t per_tile = (size_t)t.h * t.w * t.c * sizeof(float);
+    tbuf_[i].ensure(per_tile * (big_[i] ? hr_sub_ : cap));
+  }
+  for (const fsr_op& op : ops_)
+    if (op.kind == FSR_OP_HEAD) {
+      const auto& d = tensors_[op.dst];
+      headmid = std::max(headmid, (size_t)d.h * d.w * op.cout * sizeof(float) * hr_sub_);
+    }
+  if (headmid) d_headmid_.ensure(headmid);
+  const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile, lr_px = (size_t)hdr_.lr_tile * hdr_.lr_tile;
+  d_dem_norm_.ensure(hr_px * sizeof(float) * cap);
+  d_pred_norm_.ensure(hr_px * sizeof(float) * cap);
+  d_depth_norm_.ensure(lr_px * sizeof(float) * cap);
+  cap_tiles_ = cap;
+}
+
+float* Engine::tptr(int tid, int sub_start) const {
+  if (tid < 0) return nullptr;
+  const auto& t = tensors_[tid];
+  float* base = tbase_[tid];
+  if (big_[tid]) return base;
+  return base + (size_t)sub_start * t.h * t.w * t.c;
+}
+
+void Engine::run_ops(bool hr_phase, int n, int sub_start, cudaStream_t s) {
+  const float* W = d_weights_.as<float>();
+  auto wp = [&](int off) -> const float* { return off >= 0 ? W + off : nullptr; };
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    if ((op_hr_[i] != 0) != hr_phase) continue;
+    const fsr_op& op = ops_[i];
+    const auto& ts = tensors_[op.src0];
+    const auto& td = tensors_[op.dst];
+    const float* s0 = tptr(op.src0, sub_start);
+    const float* s1 = tptr(op.src1, sub_start);
+    const float* rs = tptr(op.res, sub_start);
+    float* dst = tptr(op.dst, sub_start);
+    const int c1 = op.src1 >= 0 ? tensors_[op.src1].c : 0;
+    switch (op.kind) {
+      case FSR_OP_CONV:
+        launch_conv_fp32(s0, ts.c, s1, c1, wp(op.w_off), wp(op.b_off), rs, dst, n, td.h, td.w, op.k, op.cout, op.act, op.alpha, s);
+        break;
+      case FSR_OP_POOL:
+        launch_pool_fp32(s0, dst, n, ts.h, ts.w, ts.c, op.k, op.mode, s);
+        break;
+      case FSR_OP_UPSAMPLE:
+        launch_upsample_fp32(s0, dst, n, ts.h, ts.w, ts.c, op.k, s);
+        break;
+      case FSR_OP_CONVT:
+        launch_convt_fp32(s0, wp(op.w_off), wp(op.b_off), dst, n, ts.h, ts.w, ts.c, op.cout, op.k, op.act, op.alpha, s);
+        break;
+      case FSR_OP_ELTWISE:
+        launch_eltwise_fp32(s0, s1, dst, (size_t)n * td.h * td.w * td.c, op.act, op.alpha, s);
+        break;
+      case FSR_OP_HEAD: {
+        float* mid = d_headmid_.as<float>();
+        launch_conv_fp32(s0, ts.c, s1, c1, wp(op.w_off), wp(op.b_off), nullptr, mid, n, td.h, td.w, op.k, op.cout, op.act, op.alpha, s);
+        launch_head_1x1_fp32(mid, wp(op.w2_off), wp(op.b2_off), dst, (size_t)n * td.h * td.w, op.cout, s);
+        break;
+      }
+      default:
+        throw Error(FSR_E_UNSUPPORTED, "op kind not implemented");
+    }
+  }
+}
+
+void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_norm, float* d_pred_norm, cudaStream_t s) {
+  if (n_tiles <= 0) return;
+  const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile, lr_px = (size_t)hdr_.lr_tile * hdr_.lr_tile;
+  for (int c0 = 0; c0 < n_tiles; c0 += chunk_tiles_) {
+    const int n = std::min(chunk_tiles_, n_tiles - c0);
+    ensure_arena(n);
+    for (size_t i = 0; i < tensors_.size(); ++i) tbase_[i] = tbuf_[i].as<float>();
+    tbase_[0] = const_cast<float*>(d_depth_norm) + (size_t)c0 * lr_px;
+    tbase_[1] = const_cast<float*>(d_dem_norm) + (size_t)c0 * hr_px;
+    tbase_[hdr_.out_tensor] = d_pred_norm + (size_t)c0 * hr_px;
+    run_ops(false, n, 0, s);
+    for (int sub = 0; sub < n; sub += hr_sub_) run_ops(true, std::min(hr_sub_, n - sub), sub, s);
+  }
+}
+
+void Engine::run_tiles_from_grid(const float* d_depth, const float* d_dem, const TileGrid& grid, int tile_base, int n_tiles,
+                                 const fsr_tile_params& p, float* d_pred_m, float* d_pred_norm, float* d_stats_out,
+                                 cudaStream_t s) {
+  const int T = hdr_.hr_tile, TL = hdr_.lr_tile;
+  const size_t hr_px = (size_t)T * T;
+  for (int c0 = 0; c0 < n_tiles; c0 += chunk_tiles_) {
+    const int n = std::min(chunk_tiles_, n_tiles - c0);
+    ensure_arena(n);
+    launch_tile_normalize(d_dem, d_depth, grid, tile_base + c0, n, T, TL, hdr_.scale, p, d_dem_norm_.as<float>(),
+                          d_depth_norm_.as<float>(), d_stats_out, d_flags(), s);
+    float* pn = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : d_pred_norm_.as<float>();
+    forward(n, d_depth_norm_.as<float>(), d_dem_norm_.as<float>(), pn, s);
+    launch_invert_depth(pn, d_pred_m + (size_t)c0 * hr_px, (size_t)n * hr_px, p.max_depth, p.depth_denom, s);
+  }
+}
+
+unsigned Engine::fetch_flags(cudaStream_t s) {
+  unsigned f = 0;
+  FSR_CUDA(cudaMemcpyAsync(&f, d_flags_.p, sizeof(f), cudaMemcpyDeviceToHost, s));
+  FSR_CUDA(cudaMemsetAsync(d_flags_.p, 0, sizeof(f), s));
+  FSR_CUDA(cudaStreamSynchronize(s));
+  return f;
+}
+
+static void upload_ints(DeviceBuf& b, const std::vector<int>& v, cudaStream_t s) {
+  b.ensure(std::max<size_t>(v.size(), 1) * sizeof(int));
+  if (!v.empty()) FSR_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+}
+
+void Engine::setup_windows(int H, int W, int method, int overlap, const int* ys, int ny, const int* xs, int nx,
+                           const float* ramp, cudaStream_t s) {
+  const int T = hdr_.hr_tile;
+  FSR_REQUIRE(H > 0 && W > 0 && ny > 0 && nx > 0 && ys && xs, "empty raster or window grid");
+  FSR_REQUIRE(method == FSR_WINDOW_HARD || method == FSR_WINDOW_FEATHER, "unknown window method");
+  FSR_REQUIRE(method == FSR_WINDOW_HARD || ramp != nullptr, "feather windowing needs the ramp");
+  FSR_REQUIRE(overlap >= 0 && overlap < T, "overlap must be in [0, tile)");
+  const int Hpad = ceil_div(H, T) * T, Wpad = ceil_div(W, T) * T;
+  win.H = H; win.W = W; win.T = T; win.overlap = overlap; win.method = method;
+  win.ys.assign(ys, ys + ny);
+  win.xs.assign(xs, xs + nx);
+  win.vec_ok = true;
+  auto check_axis = [&](const std::vector<int>& st, int pad, const char* name) {
+    for (size_t i = 0; i < st.size(); ++i) {
+      FSR_REQUIRE(st[i] >= 0 && st[i] + T <= pad, std::string(name) + " window origin outside the padded raster");
+      FSR_REQUIRE(i == 0 || st[i] > st[i - 1], std::string(name) + " window origins must be strictly increasing");
+      FSR_REQUIRE(st[i] % hdr_.scale == 0, std::string(name) + " window origin must be a multiple of the model scale");
+    }
+  };
+  check_axis(win.ys, Hpad, "y");
+  check_axis(win.xs, Wpad, "x");
+  for (int x : win.xs) if (x % 4) win.vec_ok = false;
+  // windows covering each padded coordinate form a contiguous index range because origins are sorted
+  auto cover = [&](const std::vector<int>& st, int pad, std::vector<int>& first, std::vector<int>& count) {
+    first.assign(pad, 0);
+    count.assign(pad, 0);
+    for (int i = (int)st.size() - 1; i >= 0; --i)
+      for (int c = st[i]; c < st[i] + T; ++c) {
+        first[c] = i;
+        count[c] += 1;
+      }
+  };
+  std::vector<int> yf, yc, xf, xc;
+  cover(win.ys, Hpad, yf, yc);
+  cover(win.xs, Wpad, xf, xc);
+  std::vector<int> org((size_t)ny * nx * 2);
+  for (int yi = 0; yi < ny; ++yi)
+    for (int xi = 0; xi < nx; ++xi) {
+      org[((size_t)yi * nx + xi) * 2 + 0] = ys[yi];
+      org[((size_t)yi * nx + xi) * 2 + 1] = xs[xi];
+    }
+  upload_ints(win.d_ys, win.ys, s);
+  upload_ints(win.d_xs, win.xs, s);
+  upload_ints(win.d_yfirst, yf, s);
+  upload_ints(win.d_ycount, yc, s);
+  upload_ints(win.d_xfirst, xf, s);
+  upload_ints(win.d_xcount, xc, s);
+  upload_ints(win.d_origins, org, s);
+  win.has_ramp = (method == FSR_WINDOW_FEATHER);
+  if (win.has_ramp) {
+    win.d_ramp.ensure((size_t)T * sizeof(float));
+    FSR_CUDA(cudaMemcpyAsync(win.d_ramp.p, ramp, (size_t)T * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  // the host vectors above are pageable temporaries: make sure the copies are done before they die
+  FSR_CUDA(cudaStreamSynchronize(s));
+}
+
+BlendGeom Engine::blend_geom() const {
+  BlendGeom g;
+  g.y_starts = win.d_ys.as<int>();
+  g.x_starts = win.d_xs.as<int>();
+  g.ny = (int)win.ys.size();
+  g.nx = (int)win.xs.size();
+  g.ramp = win.has_ramp ? win.d_ramp.as<float>() : nullptr;
+  g.y_first = win.d_yfirst.as<int>();
+  g.y_count = win.d_ycount.as<int>();
+  g.x_first = win.d_xfirst.as<int>();
+  g.x_count = win.d_xcount.as<int>();
+  g.T = win.T;
+  g.overlap = win.overlap;
+  g.H = win.H;
+  g.W = win.W;
+  g.vec_ok = win.vec_ok ? 1 : 0;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// band-level driver shared by the host and device entry points
+// ------------------------------------------------------------------------------------------------------
+
+static void band_rows(const Engine& e, int ty0, int ty1, int& row0, int& n_rows, int& halo_out) {
+  const auto& ys = e.win.ys;
+  const int ny = (int)ys.size(), T = e.win.T, H = e.win.H;
+  row0 = ty0 == 0 ? 0 : std::min(ys[ty0], H);
+  const int row_end = ty1 >= ny ? H : std::min(ys[ty1], H);
+  n_rows = std::max(row_end - row0, 0);
+  halo_out = ty1 >= ny ? 0 : std::max(std::min(ys[ty1 - 1] + T, H) - row_end, 0);
+}
+
+// d_depth/d_dem hold raster rows starting at band_row0 (HR rows; band_row0 % scale == 0), band_rows_hr of them.
+static void band_run(Engine& e, const float* d_depth, const float* d_dem, int band_row0, int band_rows_hr, int ty0, int ty1,
+                     const fsr_tile_params& p, float* d_halo_out, float* d_stats, cudaStream_t s) {
+  const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T;
+  FSR_REQUIRE(ty0 >= 0 && ty0 < ty1 && ty1 <= ny, "bad tile-row range");
+  FSR_REQUIRE(band_row0 % e.scale() == 0 && band_row0 <= e.win.ys[ty0], "band rows do not cover the band's first window");
+  const int need_end = std::min(e.win.ys[ty1 - 1] + T, e.win.H);
+  FSR_REQUIRE(band_row0 + band_rows_hr >= need_end, "band rows do not cover the band's last window");
+  const int n_tiles = (ty1 - ty0) * nx;
+  e.d_tiles.ensure((size_t)n_tiles * T * T * sizeof(float));
+  float* stats = d_stats;
+  if (!stats) {
+    e.d_stats.ensure((size_t)n_tiles * 3 * sizeof(float));
+    stats = e.d_stats.as<float>();
+  }
+  // origins local to the band's rows
+  TileGrid grid;
+  std::vector<int> org((size_t)n_tiles * 2);
+  for (int yi = ty0; yi < ty1; ++yi)
+    for (int xi = 0; xi < nx; ++xi) {
+      org[((size_t)(yi - ty0) * nx + xi) * 2 + 0] = e.win.ys[yi] - band_row0;
+      org[((size_t)(yi - ty0) * nx + xi) * 2 + 1] = e.win.xs[xi];
+    }
+  e.d_tmp_a.ensure(org.size() * sizeof(int));
+  FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaStreamSynchronize(s));
+  grid.origins = e.d_tmp_a.as<int2>();
+  grid.H = std::min(e.win.H - band_row0, band_rows_hr);
+  grid.W = e.win.W;
+  grid.Hl = ceil_div(grid.H, e.scale());
+  grid.Hl = std::min(grid.Hl, e.win.H / e.scale() - band_row0 / e.scale());
+  grid.Wl = e.win.W / e.scale();
+  e.run_tiles_from_grid(d_depth, d_dem, grid, 0, n_tiles, p, e.d_tiles.as<float>(), nullptr, stats, s);
+  int row0, n_rows, halo_out;
+  band_rows(e, ty0, ty1, row0, n_rows, halo_out);
+  e.band = BandState{ty0, ty1, row0, n_rows, halo_out, p.max_depth};
+  if (halo_out > 0 && d_halo_out) {
+    BlendGeom g = e.blend_geom();
+    launch_blend(e.d_tiles.as<float>(), ty0, ty1, g, row0 + n_rows, halo_out, nullptr, 0, false, p.max_depth, d_halo_out, s);
+  }
+}
+
+static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s) {
+  BlendGeom g = e.blend_geom();
+  launch_blend(e.d_tiles.as<float>(), e.band.ty0, e.band.ty1, g, e.band.row0, e.band.n_rows, d_halo_in, halo_rows_in, true,
+               e.band.max_depth, d_out_rows, s);
+}
+
+}  // namespace fsr
+
+// ------------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------------
+
+using namespace fsr;
+
+struct fsr_engine {
+  Engine impl;
+  fsr_engine(const void* plan, size_t pb, const float* w, size_t wc, int dev, int prec) : impl(plan, pb, w, wc, dev, prec) {}
+};
+
+#define FSR_API_BEGIN(eng)                          \
+  try {                                             \
+    if (!(eng)) throw Error(FSR_E_INVALID, "engine handle is NULL"); \
+    (eng)->impl.set_device();                       \
+    g_launch_counter = &(eng)->impl.launches;
+#define FSR_API_END()                               \
+    return FSR_OK;                                  \
+  } catch (const Error& e) {                        \
+    g_last_error = e.what();                        \
+    cudaGetLastError();                             \
+    return e.code;                                  \
+  } catch (const std::exception& e) {               \
+    g_last_error = e.what();                        \
+    return FSR_E_INVALID;                           \
+  }
+
+static void check_params(const fsr_tile_params* p, int n_px) {
+  FSR_REQUIRE(p != nullptr, "params is NULL");
+  FSR_REQUIRE(p->max_depth > 0.f && p->depth_denom > 0.f, "max_depth and depth_denom must be > 0");
+  if (p->normalize_inputs) {
+    FSR_REQUIRE(p->rank_lo >= 0 && p->rank_lo <= p->rank_hi && p->rank_hi < n_px, "percentile ranks outside the tile");
+    FSR_REQUIRE(p->gamma >= 0.f && p->gamma < 1.f, "percentile gamma must be in [0, 1)");
+  }
+}
+
+extern "C" {
+
+int fsr_abi_version(void) { return FSR_ABI_VERSION; }
+
+const char* fsr_last_error(void) { return g_last_error.c_str(); }
+
+int fsr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fsr_create(const void* plan, size_t plan_bytes, const float* weights, size_t weights_count, int device, int precision,
+               fsr_engine** out) {
+  try {
+    FSR_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    *out = new fsr_engine(plan, plan_bytes, weights, weights_count, device, precision);
+    return FSR_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return FSR_E_INVALID;
+  }
+}
+
+int fsr_destroy(fsr_engine* eng) {
+  if (!eng) return FSR_OK;
+  g_launch_counter = nullptr;
+  delete eng;
+  return FSR_OK;
+}
+
+int fsr_contract(const fsr_engine* eng, int32_t* lr_tile, int32_t* hr_tile, int32_t* scale) {
+  if (!eng) {
+    g_last_error = "engine handle is NULL";
+    return FSR_E_INVALID;
+  }
+  if (lr_tile) *lr_tile = eng->impl.lr_tile();
+  if (hr_tile) *hr_tile = eng->impl.hr_tile();
+  if (scale) *scale = eng->impl.scale();
+  return FSR_OK;
+}
+
+int64_t fsr_launch_count(const fsr_engine* eng) { return eng ? eng->impl.launches.n : 0; }
+
+int64_t fsr_macs_per_tile(const fsr_engine* eng) { return eng ? eng->impl.macs_per_tile() : 0; }
+
+int fsr_run_tiles(fsr_engine* eng, const float* depth_lr, const float* dem_hr, int32_t n_tiles, const fsr_tile_params* params,
+                  float* out_pred_m, float* out_pred_norm, float* out_stats, uint32_t* out_flags) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  const int T = e.hr_tile(), TL = e.lr_tile();
+  FSR_REQUIRE(n_tiles > 0 && depth_lr && dem_hr && out_pred_m, "empty batch or NULL buffer");
+  check_params(params, T * T);
+  const size_t hr_px = (size_t)T * T, lr_px = (size_t)TL * TL;
+  cudaStream_t s = 0;
+  e.d_in_depth.ensure(lr_px * n_tiles * sizeof(float));
+  e.d_in_dem.ensure(hr_px * n_tiles * sizeof(float));
+  e.d_tiles.ensure(hr_px * n_tiles * sizeof(float));
+  e.d_stats.ensure((size_t)n_tiles * 3 * sizeof(float));
+  if (out_pred_norm) e.d_out.ensure(hr_px * n_tiles * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, lr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, dem_hr, hr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
+  // a batch of independent tiles is the raster [n*T, T] with one window per tile
+  std::vector<int> org((size_t)n_tiles * 2);
+  for (int t = 0; t < n_tiles; ++t) {
+    org[2 * t] = t * T;
+    org[2 * t + 1] = 0;
+  }
+  e.d_tmp_a.ensure(org.size() * sizeof(int));
+  FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  TileGrid grid{e.d_tmp_a.as<int2>(), n_tiles * T, T, n_tiles * TL, TL};
+  e.run_tiles_from_grid(e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), grid, 0, n_tiles, *params, e.d_tiles.as<float>(),
+                        out_pred_norm ? e.d_out.as<float>() : nullptr, e.d_stats.as<float>(), s);
+  FSR_CUDA(cudaMemcpyAsync(out_pred_m, e.d_tiles.p, hr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out_pred_norm) FSR_CUDA(cudaMemcpyAsync(out_pred_norm, e.d_out.p, hr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)n_tiles * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  unsigned f = e.fetch_flags(s);
+  if (out_flags) *out_flags = f;
+  if (f) throw Error(FSR_E_ASSERT, "input validation failed on the device (see flags)");
+  FSR_API_END()
+}
+
+int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, int32_t H, int32_t W, int32_t window_method,
+                   int32_t overlap_hr, const int32_t* y_starts, int32_t ny, const int32_t* x_starts, int32_t nx,
+                   const float* ramp, const fsr_tile_params* params, float* out_sr, float* out_stats, uint32_t* out_flags) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  const int T = e.hr_tile(), sc = e.scale();
+  FSR_REQUIRE(depth_lr && dem_hr && out_sr && H > 0 && W > 0, "empty raster or NULL buffer");
+  check_params(params, T * T);
+  const int Hl = H / sc, Wl = W / sc;
+  FSR_REQUIRE(Hl > 0 && Wl > 0, "raster smaller than one low-resolution cell");
+  cudaStream_t s = 0;
+  e.setup_windows(H, W, window_method, overlap_hr, y_starts, ny, x_starts, nx, ramp, s);
+  e.d_in_depth.ensure((size_t)Hl * Wl * sizeof(float));
+  e.d_in_dem.ensure((size_t)H * W * sizeof(float));
+  e.d_out.ensure((size_t)H * W * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, (size_t)Hl * Wl * sizeof(float), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, dem_hr, (size_t)H * W * sizeof(float), cudaMemcpyHostToDevice, s));
+  band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), 0, H, 0, ny, *params, nullptr, nullptr, s);
+  band_finalize(e, nullptr, 0, e.d_out.as<float>(), s);
+  FSR_CUDA(cudaMemcpyAsync(out_sr, e.d_out.p, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)ny * nx * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  unsigned f = e.fetch_flags(s);
+  if (out_flags) *out_flags = f;
+  if (f) throw Error(FSR_E_ASSERT, "input validation failed on the device (see flags)");
+  FSR_API_END()
+}
+
+int fsr_set_windows(fsr_engine* eng, int32_t H, int32_t W, int32_t window_method, int32_t overlap_hr, const int32_t* y_starts,
+                    int32_t ny, const int32_t* x_starts, int32_t nx, const float* ramp, void* stream) {
+  FSR_API_BEGIN(eng)
+  eng->impl.setup_windows(H, W, window_method, overlap_hr, y_starts, ny, x_starts, nx, ramp, (cudaStream_t)stream);
+  FSR_API_END()
+}
+
+int fsr_band_geometry(fsr_engine* eng, int32_t ty0, int32_t ty1, int32_t* row0, int32_t* n_rows, int32_t* halo_out_rows,
+                      int32_t* in_row0, int32_t* in_rows) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  const int ny = (int)e.win.ys.size();
+  FSR_REQUIRE(ny > 0, "fsr_set_windows has not been called");
+  FSR_REQUIRE(ty0 >= 0 && ty0 < ty1 && ty1 <= ny, "bad tile-row range");
+  int r0, nr, ho;
+  band_rows(e, ty0, ty1, r0, nr, ho);
+  if (row0) *row0 = r0;
+  if (n_rows) *n_rows = nr;
+  if (halo_out_rows) *halo_out_rows = ho;
+  const int first = std::min(e.win.ys[ty0], e.win.H);
+  const int last = std::min(e.win.ys[ty1 - 1] + e.win.T, e.win.H);
+  if (in_row0) *in_row0 = first;
+  if (in_rows) *in_rows = std::max(last - first, 0);
+  FSR_API_END()
+}
+
+int fsr_band_run_dev(fsr_engine* eng, const float* d_depth_lr, const float* d_dem_hr, int32_t band_row0, int32_t band_rows_hr,
+                     int32_t ty0, int32_t ty1, const fsr_tile_params* params, float* d_halo_out, float* d_stats, void* stream) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  check_params(params, e.hr_tile() * e.hr_tile());
+  FSR_REQUIRE(!e.win.ys.empty(), "fsr_set_windows has not been called");
+  FSR_REQUIRE(d_depth_lr && d_dem_hr, "NULL device buffer");
+  band_run(e, d_depth_lr, d_dem_hr, band_row0, band_rows_hr, ty0, ty1, *params, d_halo_out, d_stats, (cudaStream_t)stream);
+  FSR_API_END()
+}
+
+int fsr_band_finalize_dev(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows_in, float* d_out_rows, void* stream) {
+  FSR_API_BEGIN(eng)
+  FSR_REQUIRE(d_out_rows != nullptr, "NULL device buffer");
+  FSR_REQUIRE(eng->impl.band.ty1 > eng->impl.band.ty0, "fsr_band_run_dev has not been called");
+  band_finalize(eng->impl, d_halo_in, halo_rows_in, d_out_rows, (cudaStream_t)stream);
+  FSR_API_END()
+}
+
+int fsr_fetch_flags(fsr_engine* eng, void* stream, uint32_t* out_flags) {
+  FSR_API_BEGIN(eng)
+  unsigned f = eng->impl.fetch_flags((cudaStream_t)stream);
+  if (out_flags) *out_flags = f;
+  FSR_API_END()
+}
+
+int fsr_stage_normalize(fsr_engine* eng, const float* depth_lr, const float* dem_hr, int32_t n_tiles,
+                        const fsr_tile_params* params, float* out_depth_norm, float* out_dem_norm, float* out_stats,
+                        uint32_t* out_flags) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  const int T = e.hr_tile(), TL = e.lr_tile();
+  FSR_REQUIRE(n_tiles > 0 && depth_lr && dem_hr, "empty batch or NULL buffer");
+  check_params(params, T * T);
+  const size_t hr_px = (size_t)T * T, lr_px = (size_t)TL * TL;
+  cudaStream_t s = 0;
+  e.d_in_depth.ensure(lr_px * n_tiles * sizeof(float));
+  e.d_in_dem.ensure(hr_px * n_tiles * sizeof(float));
+  e.d_tmp_b.ensure(lr_px * n_tiles * sizeof(float));
+  e.d_out.ensure(hr_px * n_tiles * sizeof(float));
+  e.d_stats.ensure((size_t)n_tiles * 3 * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, lr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, dem_hr, hr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemsetAsync(e.d_stats.p, 0, (size_t)n_tiles * 3 * sizeof(float), s));
+  std::vector<int> org((size_t)n_tiles * 2);
+  for (int t = 0; t < n_tiles; ++t) {
+    org[2 * t] = t * T;
+    org[2 * t + 1] = 0;
+  }
+  e.d_tmp_a.ensure(org.size() * sizeof(int));
+  FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  TileGrid grid{e.d_tmp_a.as<int2>(), n_tiles * T, T, n_tiles * TL, TL};
+  launch_tile_normalize(e.d_in_dem.as<float>(), e.d_in_depth.as<float>(), grid, 0, n_tiles, T, TL, e.scale(), *params,
+                        e.d_out.as<float>(), e.d_tmp_b.as<float>(), e.d_stats.as<float>(), e.d_flags(), s);
+  if (out_depth_norm) FSR_CUDA(cudaMemcpyAsync(out_depth_norm, e.d_tmp_b.p, lr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out_dem_norm) FSR_CUDA(cudaMemcpyAsync(out_dem_norm, e.d_out.p, hr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)n_tiles * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  unsigned f = e.fetch_flags(s);
+  if (out_flags) *out_flags = f;
+  if (f) throw Error(FSR_E_ASSERT, "input validation failed on the device (see flags)");
+  FSR_API_END()
+}
+
+int fsr_stage_forward(fsr_engine* eng, const float* depth_norm, const float* dem_norm, int32_t n_tiles, float* out_pred_norm) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  const int T = e.hr_tile(), TL = e.lr_tile();
+  FSR_REQUIRE(n_tiles > 0 && depth_norm && dem_norm && out_pred_norm, "empty batch or NULL buffer");
+  const size_t hr_px = (size_t)T * T, lr_px = (size_t)TL * TL;
+  cudaStream_t s = 0;
+  e.d_in_depth.ensure(lr_px * n_tiles * sizeof(float));
+  e.d_in_dem.ensure(hr_px * n_tiles * sizeof(float));
+  e.d_out.ensure(hr_px * n_tiles * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_norm, lr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, dem_norm, hr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
+  e.forward(n_tiles, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), e.d_out.as<float>(), s);
+  FSR_CUDA(cudaMemcpyAsync(out_pred_norm, e.d_out.p, hr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
+  FSR_CUDA(cudaStreamSynchronize(s));
+  FSR_API_END()
+}
+
+int fsr_stage_invert(fsr_engine* eng, const float* pred_norm, size_t n, float max_depth, float depth_denom, float* out_pred_m) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  FSR_REQUIRE(n > 0 && pred_norm && out_pred_m, "empty input or NULL buffer");
+  cudaStream_t s = 0;
+  e.d_in_dem.ensure(n * sizeof(float));
+  e.d_out.ensure(n * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, pred_norm, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  launch_invert_depth(e.d_in_dem.as<float>(), e.d_out.as<float>(), n, max_depth, depth_denom, s);
+  FSR_CUDA(cudaMemcpyAsync(out_pred_m, e.d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  FSR_CUDA(cudaStreamSynchronize(s));
+  FSR_API_END()
+}
+
+int fsr_stage_blend(fsr_engine* eng, const float* tiles, int32_t H, int32_t W, int32_t window_method, int32_t overlap_hr,
+                    const int32_t* y_starts, int32_t ny, const int32_t* x_starts, int32_t nx, const float* ramp,
+                    float max_depth, float* out_sr) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  FSR_REQUIRE(tiles && out_sr, "NULL buffer");
+  cudaStream_t s = 0;
+  e.setup_windows(H, W, window_method, overlap_hr, y_starts, ny, x_starts, nx, ramp, s);
+  const size_t tile_px = (size_t)e.hr_tile() * e.hr_tile();
+  e.d_tiles.ensure(tile_px * ny * nx * sizeof(float));
+  e.d_out.ensure((size_t)H * W * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(e.d_tiles.p, tiles, tile_px * ny * nx * sizeof(float), cudaMemcpyHostToDevice, s));
+  BlendGeom g = e.blend_geom();
+  launch_blend(e.d_tiles.as<float>(), 0, ny, g, 0, H, nullptr, 0, true, max_depth, e.d_out.as<float>(), s);
+  FSR_CUDA(cudaMemcpyAsync(out_sr, e.d_out.p, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToHost, s));
+  FSR_CUDA(cudaStreamSynchronize(s));
+  FSR_API_END()
+}
+
+void* fsr_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void fsr_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

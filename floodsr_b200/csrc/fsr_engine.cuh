@@ -1,0 +1,138 @@
+// Engine object behind the C ABI: owns the lowered plan, device weights, activation arenas and the
+// raster-level scratch (tile predictions, window geometry tables).
+#pragma once
+#include <vector>
+
+#include "fsr_common.cuh"
+
+namespace fsr {
+
+struct BlendGeom {
+  const int* y_starts;
+  const int* x_starts;
+  int ny, nx;
+  const float* ramp;     // [T] feather weights, nullptr for the hard method
+  const int* y_first;    // [Hpad] first window row covering raster row y
+  const int* y_count;    // [Hpad] number of window rows covering it
+  const int* x_first;    // [Wpad]
+  const int* x_count;
+  int T, overlap;
+  int H, W;              // cropped output extent
+  int vec_ok;            // window x-origins are multiples of 4: float4 path allowed
+};
+
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) FSR_CUDA(cudaFree(p));
+    p = nullptr;
+    bytes = 0;
+    FSR_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// kernel launchers (k_prologue.cu, k_fp32.cu, k_blend.cu)
+void launch_tile_normalize(const float* d_dem, const float* d_depth, const TileGrid& grid, int tile_base, int n_tiles,
+                           int T, int TL, int scale, const fsr_tile_params& p, float* d_dem_norm, float* d_depth_norm,
+                           float* d_stats, unsigned* d_flags, cudaStream_t stream);
+void launch_conv_fp32(const float* src0, int C0, const float* src1, int C1, const float* w, const float* bias,
+                      const float* res, float* dst, int n_img, int H, int W, int k, int cout, int act, float alpha,
+                      cudaStream_t s);
+void launch_convt_fp32(const float* src, const float* w, const float* bias, float* dst, int n_img, int Hin, int Win,
+                       int cin, int cout, int k, int act, float alpha, cudaStream_t s);
+void launch_pool_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int k, int mode, cudaStream_t s);
+void launch_upsample_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int f, cudaStream_t s);
+void launch_eltwise_fp32(const float* a, const float* b, float* dst, size_t total, int act, float alpha, cudaStream_t s);
+void launch_head_1x1_fp32(const float* feat, const float* w2, const float* b2, float* out, size_t n_pix, int cmid,
+                          cudaStream_t s);
+void launch_invert_depth(const float* pred_norm, float* pred_m, size_t n, float max_depth, float denom, cudaStream_t s);
+void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, int row0, int n_rows, const float* d_init,
+                  int init_rows, bool finalize, float max_depth, float* d_out, cudaStream_t s);
+
+// Window grid of one raster pass, resident on the device.
+struct WindowGrid {
+  int H = 0, W = 0, T = 0, overlap = 0, method = 0;
+  std::vector<int> ys, xs;
+  bool vec_ok = true;  // all window x-origins are multiples of 4 pixels
+  DeviceBuf d_ys, d_xs, d_ramp, d_yfirst, d_ycount, d_xfirst, d_xcount, d_origins;
+  bool has_ramp = false;
+  void release() {
+    d_ys.release(); d_xs.release(); d_ramp.release(); d_yfirst.release(); d_ycount.release();
+    d_xfirst.release(); d_xcount.release(); d_origins.release();
+  }
+};
+
+// Band geometry remembered between fsr_band_run_dev and fsr_band_finalize_dev.
+struct BandState {
+  int ty0 = 0, ty1 = 0, row0 = 0, n_rows = 0, halo_out_rows = 0;
+  float max_depth = 0.f;
+};
+
+class Engine {
+ public:
+  BandState band;
+  Engine(const void* plan, size_t plan_bytes, const float* weights, size_t weights_count, int device, int precision);
+  ~Engine();
+
+  int lr_tile() const { return hdr_.lr_tile; }
+  int hr_tile() const { return hdr_.hr_tile; }
+  int scale() const { return hdr_.scale; }
+  int64_t macs_per_tile() const;
+  LaunchCounter launches;
+
+  // network forward on normalised inputs resident on the device: [n,lr,lr] + [n,hr,hr] -> [n,hr,hr]
+  void forward(int n_tiles, const float* d_depth_norm, const float* d_dem_norm, float* d_pred_norm, cudaStream_t s);
+
+  // a5-a11 for tiles described by `grid` origins [tile_base, tile_base+n): writes metres (and optionally
+  // the raw normalised prediction) per tile, stats at d_stats[(tile_base+i)*3]
+  void run_tiles_from_grid(const float* d_depth, const float* d_dem, const TileGrid& grid, int tile_base, int n_tiles,
+                           const fsr_tile_params& p, float* d_pred_m, float* d_pred_norm, float* d_stats, cudaStream_t s);
+
+  void setup_windows(int H, int W, int method, int overlap, const int* ys, int ny, const int* xs, int nx,
+                     const float* ramp, cudaStream_t s);
+  BlendGeom blend_geom() const;
+
+  void set_device() const { FSR_CUDA(cudaSetDevice(device_)); }
+  unsigned fetch_flags(cudaStream_t s);
+  unsigned* d_flags() const { return d_flags_.as<unsigned>(); }
+
+  WindowGrid win;
+  DeviceBuf d_tiles;      // [n_tiles][T*T] per-window predictions in metres
+  DeviceBuf d_stats;      // [n_tiles][3]
+  DeviceBuf d_in_depth, d_in_dem, d_out;  // staging for the host-buffer entry points
+  DeviceBuf d_tmp_a, d_tmp_b;
+
+ private:
+  void ensure_arena(int n_tiles);
+  void run_ops(bool hr_phase, int n, int sub_start, cudaStream_t s);
+  float* tptr(int tid, int sub_start) const;
+
+  fsr_plan_header hdr_{};
+  std::vector<fsr_tensor_desc> tensors_;
+  std::vector<fsr_op> ops_;
+  std::vector<char> big_;        // tensor is an HR feature map (only allocated for hr_sub_ tiles)
+  std::vector<char> op_hr_;      // op touches a big tensor
+  int device_ = 0, precision_ = 0;
+  int cap_tiles_ = 0;            // arena capacity (tiles per chunk)
+  int hr_sub_ = 4;               // tiles per HR sub-chunk
+  int chunk_tiles_ = 64;
+  DeviceBuf d_weights_, d_flags_, d_headmid_;
+  std::vector<DeviceBuf> tbuf_;
+  std::vector<float*> tbase_;    // per-forward tensor base pointers (inputs/outputs alias caller buffers)
+  DeviceBuf d_dem_norm_, d_depth_norm_, d_pred_norm_;
+};
+
+}  // namespace fsr

@@ -1,0 +1,170 @@
+"""Row-band sharding of one raster across the GPUs of a box.
+
+The reference is single-process (`floodsr/models/ResUNet_16x_DEM.py:307-356` is a serial Python loop), so
+this is new: the window grid's tile rows are split into contiguous bands, one rank per band.  Every window
+is independent (tile-local DEM stats), so the only data exchanged is, per band boundary, the partial sums
+`sum(pred * w)` of the output rows that the upper band's last windows share with the lower band — one
+point-to-point transfer of `halo_rows x W` float32 from rank r to rank r+1.  Feather weights are analytic
+and recomputed locally.  The receiving band continues the sum in the reference's window order, so the
+sharded raster is bit-identical to the single-GPU one.
+
+The exchange itself goes through `torch.distributed` (NCCL on GPUs, gloo in the CPU tests); the band
+arithmetic is delegated to an executor (the CUDA engine in production).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from floodsr_b200.tiling import build_feather_ramp, split_tile_rows, window_grid
+
+
+@dataclass(frozen=True)
+class BandPlan:
+    rank: int
+    ty0: int
+    ty1: int
+    row0: int           # first output row owned by the band
+    n_rows: int         # output rows owned
+    halo_out_rows: int  # rows below the band that its windows also touch (sent to the next band)
+    halo_in_rows: int   # rows at the top of the band that the previous band's windows touch (received)
+    in_row0: int        # raster rows read by the band's windows: [in_row0, in_row0 + in_rows)
+    in_rows: int
+
+    @property
+    def empty(self) -> bool:
+        return self.ty1 <= self.ty0
+
+
+def plan_bands(h: int, w: int, hr_tile: int, window_method: str, overlap_hr: int, world: int) -> tuple[list[BandPlan], list[int], list[int]]:
+    """Partition the window grid of an `h x w` raster into `world` row bands (trailing bands may be empty)."""
+    ys, xs = window_grid(h, w, hr_tile, window_method, overlap_hr)
+    ny = len(ys)
+    plans: list[BandPlan] = []
+    prev_halo = 0
+    for rank, (ty0, ty1) in enumerate(split_tile_rows(ny, world)):
+        if ty1 <= ty0:
+            plans.append(BandPlan(rank, ty0, ty1, h, 0, 0, 0, h, 0))
+            continue
+        row0 = 0 if ty0 == 0 else min(ys[ty0], h)
+        row_end = h if ty1 >= ny else min(ys[ty1], h)
+        halo_out = 0 if ty1 >= ny else max(min(ys[ty1 - 1] + hr_tile, h) - row_end, 0)
+        in_row0 = min(ys[ty0], h)
+        in_end = min(ys[ty1 - 1] + hr_tile, h)
+        plans.append(BandPlan(rank, ty0, ty1, row0, max(row_end - row0, 0), halo_out, prev_halo, in_row0, max(in_end - in_row0, 0)))
+        prev_halo = halo_out
+    return plans, ys, xs
+
+
+def exchange_halo(plan: BandPlan, plans: list[BandPlan], halo_out, make_recv, dist_mod, group=None):
+    """Send this band's halo partial sums to the next band and receive the previous band's.
+
+    `halo_out`: tensor [halo_out_rows, W] or None; `make_recv(rows)` allocates the receive tensor.
+    Returns the received tensor or None.  Uses one batched isend/irecv pair (NCCL groups them).
+    """
+    ops = []
+    recv = None
+    nxt = plan.rank + 1
+    if not plan.empty and plan.halo_out_rows > 0 and nxt < len(plans) and not plans[nxt].empty:
+        ops.append(dist_mod.P2POp(dist_mod.isend, halo_out, nxt, group=group))
+    if not plan.empty and plan.halo_in_rows > 0 and plan.rank > 0:
+        recv = make_recv(plan.halo_in_rows)
+        ops.append(dist_mod.P2POp(dist_mod.irecv, recv, plan.rank - 1, group=group))
+    if ops:
+        for req in dist_mod.batch_isend_irecv(ops):
+            req.wait()
+    return recv
+
+
+class CudaBandExecutor:
+    """Band arithmetic on the CUDA engine: inputs/outputs are torch CUDA tensors owned by the caller."""
+
+    def __init__(self, engine, h: int, w: int, window_method: str, overlap_hr: int, max_depth: float = 5.0, dem_pct_clip: float = 95.0):
+        import torch
+
+        from floodsr_b200 import _lib
+
+        self.torch = torch
+        self.lib = _lib.load_library()
+        self._lib_mod = _lib
+        self.engine = engine
+        self.h, self.w = int(h), int(w)
+        c = engine.contract
+        self.hr_tile, self.scale = c.dem_hr_hwc[0], c.scale
+        self.window_method, self.overlap_hr = window_method, int(overlap_hr)
+        self.ys, self.xs = window_grid(h, w, self.hr_tile, window_method, overlap_hr)
+        self.ramp = build_feather_ramp(self.hr_tile, overlap_hr) if window_method == "feather" else None
+        self.params = engine._tile_params(max_depth, dem_pct_clip, None, None, None, True)
+        self.device = torch.device("cuda", engine.device)
+        self._windows_set = False
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_windows(self):
+        if self._windows_set:
+            return
+        ys = np.asarray(self.ys, np.int32)
+        xs = np.asarray(self.xs, np.int32)
+        self._lib_mod.check(
+            self.lib.fsr_set_windows(
+                self.engine._handle, self.h, self.w,
+                self._lib_mod.WINDOW_FEATHER if self.window_method == "feather" else self._lib_mod.WINDOW_HARD,
+                self.overlap_hr, self._lib_mod.iptr(ys), len(ys), self._lib_mod.iptr(xs), len(xs),
+                self._lib_mod.fptr(self.ramp) if self.ramp is not None else None, self._stream(),
+            )
+        )
+        self._windows_set = True
+
+    def band_run(self, plan: BandPlan, depth_band, dem_band, band_row0: int):
+        """depth_band / dem_band: CUDA float32 tensors holding raster rows from HR row `band_row0` on."""
+        torch = self.torch
+        self.set_windows()
+        assert dem_band.is_cuda and dem_band.dtype == torch.float32 and dem_band.is_contiguous()
+        assert depth_band.is_cuda and depth_band.dtype == torch.float32 and depth_band.is_contiguous()
+        halo = None
+        if plan.halo_out_rows > 0:
+            halo = torch.empty((plan.halo_out_rows, self.w), dtype=torch.float32, device=self.device)
+        self._lib_mod.check(
+            self.lib.fsr_band_run_dev(
+                self.engine._handle, C.c_void_p(depth_band.data_ptr()), C.c_void_p(dem_band.data_ptr()), int(band_row0),
+                int(dem_band.shape[0]), plan.ty0, plan.ty1, C.byref(self.params),
+                C.c_void_p(halo.data_ptr()) if halo is not None else None, None, self._stream(),
+            )
+        )
+        return halo
+
+    def band_finalize(self, plan: BandPlan, halo_in, out_rows=None):
+        torch = self.torch
+        if out_rows is None:
+            out_rows = torch.empty((plan.n_rows, self.w), dtype=torch.float32, device=self.device)
+        assert out_rows.shape == (plan.n_rows, self.w) and out_rows.is_contiguous()
+        self._lib_mod.check(
+            self.lib.fsr_band_finalize_dev(
+                self.engine._handle, C.c_void_p(halo_in.data_ptr()) if halo_in is not None else None,
+                int(halo_in.shape[0]) if halo_in is not None else 0, C.c_void_p(out_rows.data_ptr()), self._stream(),
+            )
+        )
+        return out_rows
+
+    def make_recv(self, rows: int):
+        return self.torch.empty((rows, self.w), dtype=self.torch.float32, device=self.device)
+
+    def check_flags(self):
+        flags = C.c_uint32(0)
+        self._lib_mod.check(self.lib.fsr_fetch_flags(self.engine._handle, self._stream(), C.byref(flags)))
+        self.engine._raise_flags(int(flags.value), True, None)
+
+
+def run_band_step(executor, plan: BandPlan, plans: list[BandPlan], depth_band, dem_band, band_row0: int, dist_mod=None, group=None, out_rows=None):
+    """One rank's share of a sharded raster pass: run the band, exchange halos, blend the owned rows."""
+    if plan.empty:
+        return None
+    halo_out = executor.band_run(plan, depth_band, dem_band, band_row0)
+    halo_in = None
+    if dist_mod is not None and len(plans) > 1:
+        halo_in = exchange_halo(plan, plans, halo_out, executor.make_recv, dist_mod, group)
+    return executor.band_finalize(plan, halo_in, out_rows)

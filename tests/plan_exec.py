@@ -1,0 +1,66 @@
+"""Test helper: execute a lowered plan (floodsr_b200.graph.LoweredModel) with torch CPU ops.
+
+Only used to check the ONNX -> plan lowering without a GPU; it deliberately mirrors what the CUDA engine
+does op by op (NHWC tensors, HWIO weights, fused bias/residual/activation, fused head).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from floodsr_b200 import graph as G
+
+
+def _act(x, op):
+    if op.act == G.ACT_RELU:
+        return torch.relu(x)
+    if op.act == G.ACT_LEAKY:
+        return F.leaky_relu(x, op.alpha)
+    return x
+
+
+def _conv(x_nhwc, w_hwio, bias, k):
+    x = x_nhwc.permute(0, 3, 1, 2)
+    w = torch.from_numpy(np.ascontiguousarray(w_hwio)).permute(3, 2, 0, 1)
+    b = torch.from_numpy(bias) if bias is not None else None
+    return F.conv2d(x, w, b, padding=k // 2).permute(0, 2, 3, 1)
+
+
+def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray) -> np.ndarray:
+    """depth_norm [B,lr,lr], dem_norm [B,hr,hr] -> pred_norm [B,hr,hr]."""
+    t: dict[int, torch.Tensor] = {
+        0: torch.from_numpy(np.asarray(depth_norm, np.float32))[..., None],
+        1: torch.from_numpy(np.asarray(dem_norm, np.float32))[..., None],
+    }
+    with torch.no_grad():
+        for op in lm.ops:
+            if op.kind in (G.OP_CONV, G.OP_HEAD):
+                x = t[op.src0] if op.src1 < 0 else torch.cat([t[op.src0], t[op.src1]], dim=3)
+                y = _conv(x, op.weight, op.bias, op.k)
+                if op.res >= 0:
+                    y = y + t[op.res]
+                y = _act(y, op)
+                if op.kind == G.OP_HEAD:
+                    y = (y * torch.from_numpy(op.weight2)).sum(dim=3, keepdim=True)
+                    if op.bias2 is not None:
+                        y = y + float(op.bias2.reshape(-1)[0])
+            elif op.kind == G.OP_POOL:
+                x = t[op.src0].permute(0, 3, 1, 2)
+                y = (F.max_pool2d(x, op.k) if op.mode == 0 else F.avg_pool2d(x, op.k)).permute(0, 2, 3, 1)
+            elif op.kind == G.OP_UPSAMPLE:
+                y = t[op.src0].repeat_interleave(op.k, dim=1).repeat_interleave(op.k, dim=2)
+            elif op.kind == G.OP_CONVT:
+                x = t[op.src0].permute(0, 3, 1, 2)
+                w = torch.from_numpy(np.ascontiguousarray(op.weight)).permute(2, 3, 0, 1)  # [kh,kw,ci,co] -> [ci,co,kh,kw]
+                b = torch.from_numpy(op.bias) if op.bias is not None else None
+                y = _act(F.conv_transpose2d(x, w, b, stride=op.k).permute(0, 2, 3, 1), op)
+            elif op.kind == G.OP_ELTWISE:
+                y = t[op.src0] if op.src1 < 0 else t[op.src0] + t[op.src1]
+                y = _act(y, op)
+            else:
+                raise AssertionError(op.kind)
+            assert tuple(y.shape[1:]) == lm.tensors[op.dst], (op.name, y.shape, lm.tensors[op.dst])
+            t[op.dst] = y.contiguous()
+    return t[lm.out_tensor][..., 0].numpy()

@@ -1,0 +1,331 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (run on the B200 box: -m gpu).
+
+Bit-exact: window geometry, DEM statistics and normalisation, mosaic arithmetic.  Tolerance-level: anything
+through log1p/expm1 (libm vs CUDA differ in the last ulp) and the network forward (fp32 <= 1e-4 m).
+"""
+
+from __future__ import annotations
+
+import importlib.util
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from floodsr_b200.synth import synth_dem, synth_depth, synth_raster, synth_tile
+
+pytestmark = pytest.mark.gpu
+
+_spec = importlib.util.spec_from_file_location("make_golden", Path(__file__).parent / "golden" / "make_golden.py")
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+
+FP32_TOL_M = 1e-4  # north star: fp32 predictions within 1e-4 m of the reference CPU path
+
+
+@pytest.fixture(scope="module")
+def engine(h1_model_fp):
+    from floodsr_b200.engine import EngineB200
+
+    eng = EngineB200(h1_model_fp, precision="fp32")
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_engine(h1_model_fp):
+    from oracle.engine_ref import OracleEngine
+
+    return OracleEngine(h1_model_fp)
+
+
+def _hex(stats):
+    return {k: float(v).hex() for k, v in stats.items()}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a5-a8: per-tile normalisation
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("case", mg.tile_cases(), ids=lambda c: c[0])
+def test_normalize_stage_matches_reference_golden_bit_exact(engine, golden, case):
+    from oracle import preprocessing_np as pp
+
+    meta, arrays = golden
+    name, depth, dem, kw = case
+    g = meta["cases"][f"pre/{name}"]
+    got = engine.stage_normalize(depth[None], dem[None], **kw)
+    stats = {"p_clip": float(got["stats"][0, 0]), "dem_min": float(got["stats"][0, 1]), "dem_max": float(got["stats"][0, 2])}
+    assert _hex(stats) == g["stats"]  # exact np.nanpercentile / min / max
+    assert mg.digest(got["dem_norm"][0]) == g["dem_norm_sha"]  # bit-exact normalised DEM
+    want_depth = pp.scale_depth_log1p(pp.replace_nodata_with_zero(depth, kw.get("depth_lr_nodata")), kw.get("max_depth", 5.0))
+    assert np.abs(got["depth_norm"][0] - want_depth).max() <= 2.4e-7  # log1pf vs libm: <= 2 ulp at 1.0
+
+
+def test_normalize_stage_random_tiles_vs_oracle(engine):
+    from oracle import preprocessing_np as pp
+
+    rng = np.random.default_rng(5)
+    b = 6
+    dem = np.stack([synth_dem(512, 512, seed=100 + i) * np.float32(rng.choice([1.0, 1e-3, 7.5])) for i in range(b)])
+    dem[1, 100:, :] = 0.0  # zero padding
+    dem[2] = np.round(dem[2], 0)  # heavy ties
+    depth = np.stack([synth_depth(32, 32, seed=100 + i) for i in range(b)])
+    for pct in (95.0, 37.5, 100.0):
+        got = engine.stage_normalize(depth, dem, dem_pct_clip=pct)
+        for i in range(b):
+            want, st = pp.normalize_dem(dem[i], pct)
+            assert (float(got["stats"][i, 0]), float(got["stats"][i, 1]), float(got["stats"][i, 2])) == (
+                st["p_clip"], st["dem_min"], st["dem_max"]), (pct, i)
+            assert np.array_equal(got["dem_norm"][i], want), (pct, i)
+
+
+def test_normalize_stage_ref_stats_and_errors(engine):
+    from oracle import preprocessing_np as pp
+
+    depth, dem = synth_tile(9)
+    ref = {"p_clip": 900.0, "dem_min": 250.0, "dem_max": 900.0}
+    got = engine.stage_normalize(depth[None], dem[None], dem_ref_stats=ref)
+    assert np.array_equal(got["dem_norm"][0], pp.normalize_dem(dem, ref_stats=ref)[0])
+    with pytest.raises(AssertionError, match=r"DEM range must be > 0; got min=7.0, max=7.0"):
+        engine.stage_normalize(depth[None], np.full((1, 512, 512), 7.0, np.float32))
+    bad = dem.copy()
+    bad[17, 33] = np.nan
+    with pytest.raises(AssertionError, match="DEM contains non-finite values after nodata replacement"):
+        engine.stage_normalize(depth[None], bad[None])
+    badd = depth.copy()
+    badd[3, 3] = np.inf
+    with pytest.raises(AssertionError, match="low-res depth contains non-finite values after nodata replacement"):
+        engine.stage_normalize(badd[None], dem[None])
+    with pytest.raises(AssertionError, match="dem_pct_clip must be finite"):
+        engine.stage_normalize(depth[None], dem[None], dem_pct_clip=0.0)
+    # the engine is still usable after a failed call
+    assert np.array_equal(engine.stage_normalize(depth[None], dem[None])["dem_norm"][0], pp.normalize_dem(dem)[0])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a11, a15: invert + mosaic
+# ---------------------------------------------------------------------------------------------------------
+
+
+def test_invert_stage_close_to_numpy(engine):
+    from oracle import preprocessing_np as pp
+
+    x = np.linspace(-0.2, 1.2, 200_001, dtype=np.float32)
+    for d in (5.0, 3.0):
+        got = engine.stage_invert(x, d)
+        want = pp.invert_depth_log1p(x, d)
+        assert np.abs(got - want).max() <= 2e-6  # expm1f vs libm expm1 on values up to D
+        assert got.min() == 0.0 and got.max() == np.float32(d)
+
+
+class _ReplayEngine:
+    """Feeds pre-computed tiles to the oracle's tile loop in window order."""
+
+    def __init__(self, tiles):
+        self.tiles, self.i = tiles, 0
+
+    def run_tile(self, depth, dem, **kw):
+        t = self.tiles[self.i]
+        self.i += 1
+        return {"prediction_m": t, "dem_stats_used": {"p_clip": 1.0, "dem_min": 0.0, "dem_max": 1.0}}
+
+
+@pytest.mark.parametrize(
+    "h,w,method,ov",
+    [(1024, 1536, "feather", 8), (1024, 1536, "hard", 8), (976, 1104, "feather", 8), (976, 1104, "feather", 4),
+     (528, 1296, "feather", 12), (512, 512, "feather", 8), (1000, 1100, "feather", 8), (2000, 600, "hard", 8)],
+)
+def test_blend_stage_bit_exact_vs_oracle(engine, h, w, method, ov):
+    from floodsr_b200.tiling import window_grid
+    from oracle.stitch_np import run_tiled
+
+    ys, xs = window_grid(h, w, 512, method, ov * 16)
+    rng = np.random.default_rng(h * 7 + w)
+    tiles = (rng.random((len(ys) * len(xs), 512, 512), dtype=np.float32) * 6.0 - 0.5).astype(np.float32)
+    depth = np.zeros((h // 16, w // 16), np.float32)
+    dem = np.zeros((h, w), np.float32)
+    want, n_tiles, _ = run_tiled(_ReplayEngine(tiles), depth, dem, window_method=method, overlap_lr=ov)
+    got = engine.stage_blend(tiles, h, w, method, ov)
+    assert n_tiles == len(tiles)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a10: network forward
+# ---------------------------------------------------------------------------------------------------------
+
+
+def test_forward_stage_fp32_close_to_oracle(engine, oracle_engine):
+    from oracle import preprocessing_np as pp
+
+    b = 3
+    dn = np.stack([pp.scale_depth_log1p(synth_depth(32, 32, seed=20 + i), 5.0) for i in range(b)])
+    en = np.stack([pp.normalize_dem(synth_dem(512, 512, seed=20 + i))[0] for i in range(b)])
+    want = oracle_engine.forward_norm(dn, en)
+    got = engine.stage_forward(dn, en)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.abs(got - want).max() <= 1e-5  # normalised units; x10.75 m/unit worst-case gain -> 1e-4 m
+    assert want.std() > 0.02
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a1-a4: the engine contract (mirror of the reference's tests/test_engine_contracts.py:63-93)
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("repeat_run", [False, True], ids=["b200_contract_single_run", "b200_contract_repeat_run_is_deterministic"])
+def test_engine_b200_run_tile_contract(h1_model_fp, ort_tile_inputs, repeat_run):
+    from floodsr_b200.engine import EngineB200
+
+    eng = EngineB200(h1_model_fp)
+    run1 = eng.run_tile(
+        ort_tile_inputs["depth_lr"], ort_tile_inputs["dem_hr"],
+        depth_lr_nodata=ort_tile_inputs["depth_lr_nodata"], dem_hr_nodata=ort_tile_inputs["dem_hr_nodata"],
+    )
+    assert run1["prediction_m"].dtype == np.float32
+    assert run1["prediction_m"].size > 0
+    assert set(run1) == {"prediction_m", "prediction_norm", "dem_stats_used", "runtime_s"}
+    assert run1["dem_stats_used"] == {"p_clip": 975.0, "dem_min": 500.0, "dem_max": 975.0}
+    if repeat_run:
+        run2 = eng.run_tile(
+            ort_tile_inputs["depth_lr"], ort_tile_inputs["dem_hr"],
+            depth_lr_nodata=ort_tile_inputs["depth_lr_nodata"], dem_hr_nodata=ort_tile_inputs["dem_hr_nodata"],
+        )
+        assert isinstance(run2["prediction_m"], np.ndarray)
+        assert np.array_equal(run1["prediction_m"], run2["prediction_m"])
+    assert eng.model_path() == Path(h1_model_fp).resolve()
+    assert (eng.contract.scale, eng.contract.depth_lr_hwc, eng.contract.dem_hr_hwc) == (16, (32, 32, 1), (512, 512, 1))
+    eng.close()
+    assert eng.session is None and eng.contract is None
+
+
+@pytest.mark.parametrize("case", mg.tile_cases(), ids=lambda c: c[0])
+def test_run_tile_matches_oracle(engine, oracle_engine, case):
+    name, depth, dem, kw = case
+    want = oracle_engine.run_tile(depth, dem, **kw)
+    got = engine.run_tile(depth, dem, **kw)
+    assert got["dem_stats_used"] == want["dem_stats_used"]
+    assert np.abs(got["prediction_norm"] - want["prediction_norm"]).max() <= 1e-5
+    assert np.abs(got["prediction_m"] - want["prediction_m"]).max() <= FP32_TOL_M
+    assert np.array_equal(got["prediction_m"] > 0.01, want["prediction_m"] > 0.01) or (
+        np.abs(got["prediction_m"] - want["prediction_m"])[(got["prediction_m"] > 0.01) != (want["prediction_m"] > 0.01)].max() < 1e-5
+    )
+
+
+def test_run_tile_prenormalised_branch_and_shape_errors(engine, oracle_engine):
+    from oracle import preprocessing_np as pp
+
+    depth, dem = synth_tile(0)
+    dn, en = pp.scale_depth_log1p(depth, 5.0), pp.normalize_dem(dem)[0]
+    want = oracle_engine.run_tile(dn, en, normalize_inputs=False)
+    got = engine.run_tile(dn, en, normalize_inputs=False)
+    assert got["dem_stats_used"] == want["dem_stats_used"] == {"p_clip": 95.0, "dem_min": 0.0, "dem_max": 1.0}
+    assert np.abs(got["prediction_m"] - want["prediction_m"]).max() <= FP32_TOL_M
+    with pytest.raises(AssertionError, match=r"DEM tile must be normalized to \[0, 1\]"):
+        engine.run_tile(dn, dem, normalize_inputs=False)
+    with pytest.raises(AssertionError, match=r"depth tensor shape \(16, 16, 1\) != expected \(32, 32, 1\)"):
+        engine.run_tile(depth[:16, :16], dem)
+    with pytest.raises(AssertionError, match=r"DEM tensor shape"):
+        engine.run_tile(depth, dem[:256])
+
+
+def test_run_tiles_batch_equals_single_tiles(engine):
+    b = 5
+    depth = np.stack([synth_depth(32, 32, seed=40 + i) for i in range(b)])
+    dem = np.stack([synth_dem(512, 512, seed=40 + i) for i in range(b)])
+    batch = engine.run_tiles(depth, dem)
+    for i in range(b):
+        one = engine.run_tile(depth[i], dem[i])
+        assert np.array_equal(batch["prediction_m"][i], one["prediction_m"])
+        assert batch["dem_stats_used"][i] == one["dem_stats_used"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a15: whole raster
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("h,w,method,ov", [(1024, 1536, "feather", 8), (976, 1104, "feather", 8), (976, 1104, "hard", 8)])
+def test_run_raster_matches_oracle_tile_loop(engine, oracle_engine, h, w, method, ov):
+    from oracle.stitch_np import run_tiled
+
+    depth, dem = synth_raster(h, w, seed=h + w)
+    want, n_tiles, summary = run_tiled(oracle_engine, depth, dem, window_method=method, overlap_lr=ov)
+    got, got_n, got_summary = engine.run_raster(depth, dem, window_method=method, overlap_lr=ov)
+    assert got.shape == want.shape == (h, w) and got.dtype == np.float32
+    assert got_n == n_tiles
+    assert got_summary == summary  # per-tile DEM stats are bit-exact, so is their float32 summary
+    assert np.abs(got - want).max() <= FP32_TOL_M
+    assert float(got.min()) >= 0.0 and float(got.max()) <= 5.0
+
+
+def test_run_raster_properties_at_mersch_size(engine):
+    """BASELINE config 2 size (4096 x 4096 model space, 121 feather windows): size-independent properties."""
+    h = w = 4096
+    depth, dem = synth_raster(h, w, seed=77)
+    out1, n_tiles, summary = engine.run_raster(depth, dem)
+    assert n_tiles == 121 and summary["tile_count"] == 121.0
+    assert out1.shape == (h, w) and np.isfinite(out1).all() and out1.min() >= 0.0 and out1.max() <= 5.0
+    out2, _, _ = engine.run_raster(depth, dem)
+    assert np.array_equal(out1, out2)  # deterministic: no atomics anywhere in the path
+    # hard mosaic == the batched tiles pasted side by side
+    hard, n_hard, _ = engine.run_raster(depth, dem, window_method="hard")
+    assert n_hard == 64
+    d_t = depth.reshape(8, 32, 8, 32).transpose(0, 2, 1, 3).reshape(64, 32, 32)
+    e_t = dem.reshape(8, 512, 8, 512).transpose(0, 2, 1, 3).reshape(64, 512, 512)
+    tiles = engine.run_tiles(d_t, e_t, want_norm=False)["prediction_m"]
+    pasted = tiles.reshape(8, 8, 512, 512).transpose(0, 2, 1, 3).reshape(h, w)
+    assert np.array_equal(hard, pasted)
+    # interior of non-overlapped regions of the feather mosaic equals the hard tile there
+    assert np.array_equal(out1[:384, :384], hard[:384, :384])
+
+
+def test_run_raster_input_assertions(engine):
+    depth, dem = synth_raster(1024, 1024, seed=3)
+    with pytest.raises(AssertionError, match="depth shape"):
+        engine.run_raster(depth[:-1], dem)
+    with pytest.raises(AssertionError, match="aligned DEM must be 2D"):
+        engine.run_raster(depth, dem[None])
+    bad = dem.copy()
+    bad[5, 5] = np.inf
+    with pytest.raises(AssertionError, match="aligned DEM contains non-finite values"):
+        engine.run_raster(depth, bad)
+    with pytest.raises(AssertionError, match="unsupported window_method"):
+        engine.run_raster(depth, dem, window_method="soft")
+    with pytest.raises(AssertionError, match="feather windowing requires overlap_lr > 0"):
+        engine.run_raster(depth, dem, overlap_lr=0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# row-band sharding on one device: two bands run back to back must reproduce the single pass bit for bit
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("h,w,world", [(2048, 1024, 2), (1552, 1040, 3), (4096, 1024, 4)])
+def test_band_sharding_is_bit_identical_to_single_pass(engine, h, w, world):
+    import torch
+
+    from floodsr_b200.dist import CudaBandExecutor, plan_bands
+
+    depth, dem = synth_raster(h, w, seed=h)
+    want, _, _ = engine.run_raster(depth, dem)
+    plans, ys, xs = plan_bands(h, w, 512, "feather", 128, world)
+    ex = CudaBandExecutor(engine, h, w, "feather", 128)
+    dev = torch.device("cuda", engine.device)
+    got = np.empty_like(want)
+    halo = None
+    for plan in plans:
+        if plan.empty:
+            continue
+        r0 = plan.in_row0
+        dem_band = torch.from_numpy(dem[r0 : r0 + plan.in_rows]).to(dev).contiguous()
+        depth_band = torch.from_numpy(depth[r0 // 16 : (r0 + plan.in_rows + 15) // 16]).to(dev).contiguous()
+        halo_out = ex.band_run(plan, depth_band, dem_band, r0)
+        assert (halo is None) == (plan.halo_in_rows == 0)
+        rows = ex.band_finalize(plan, halo)
+        ex.check_flags()
+        got[plan.row0 : plan.row0 + plan.n_rows] = rows.cpu().numpy()
+        halo = halo_out
+    assert np.array_equal(got, want)
