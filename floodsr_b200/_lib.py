@@ -17,6 +17,7 @@ FSR_OK, FSR_E_INVALID, FSR_E_CUDA, FSR_E_ASSERT, FSR_E_UNSUPPORTED = 0, -1, -2, 
 PREC_FP32, PREC_BF16 = 0, 1
 WINDOW_HARD, WINDOW_FEATHER = 0, 1
 FLAG_DEPTH_NONFINITE, FLAG_DEM_NONFINITE, FLAG_DEM_FLAT_NONZERO, FLAG_DEPTH_NOT_UNIT, FLAG_DEM_NOT_UNIT = 1, 2, 4, 8, 16
+PROF_CATEGORIES = ("normalize", "lr_conv", "lr_misc", "convt", "head", "invert", "blend")
 
 
 class TileParams(C.Structure):
@@ -79,6 +80,10 @@ SIGNATURES = {
         C.c_int,
         [_H, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I, C.c_int32, _I, C.c_int32, _F, C.c_float, _F],
     ),
+    "fsr_profile_enable": (C.c_int, [_H, C.c_int32]),
+    "fsr_profile_fetch": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "fsr_debug_tensor_shape": (C.c_int, [_H, C.c_int32, _I, _I, _I]),
+    "fsr_debug_read_tensor": (C.c_int, [_H, C.c_int32, C.c_int32, _F]),
     "fsr_host_alloc": (C.c_void_p, [C.c_size_t]),
     "fsr_host_free": (None, [C.c_void_p]),
 }

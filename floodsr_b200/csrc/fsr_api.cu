@@ -74,7 +74,13 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_CUDA(cudaMemset(d_flags_.p, 0, sizeof(unsigned)));
   tbuf_.resize(tensors_.size());
   tbase_.assign(tensors_.size(), nullptr);
-  if (precision_ == FSR_PREC_BF16) throw Error(FSR_E_UNSUPPORTED, "bf16 tensor-core backend is not built into this library yet");
+  if (precision_ == FSR_PREC_BF16) {
+    cudaDeviceProp prop;
+    FSR_CUDA(cudaGetDeviceProperties(&prop, device_));
+    if (prop.major != 10) throw Error(FSR_E_UNSUPPORTED, "the bf16 backend needs an sm_100 (Blackwell) device: tcgen05/TMEM/TMA");
+    chunk_tiles_ = 256;
+    tc_prepare(weights);
+  }
 }
 
 Engine::~Engine() {
@@ -105,6 +111,15 @@ void Engine::ensure_arena(int n_tiles) {
   if (n_tiles <= cap_tiles_) return;
   const int cap = std::max(n_tiles, chunk_tiles_);
   size_t headmid = 0;
+  const size_t hr_px0 = (size_t)hdr_.hr_tile * hdr_.hr_tile, lr_px0 = (size_t)hdr_.lr_tile * hdr_.lr_tile;
+  if (precision_ == FSR_PREC_BF16) {
+    tc_ensure_arena(cap);
+    d_dem_norm_.ensure(hr_px0 * sizeof(float) * cap);
+    d_pred_norm_.ensure(hr_px0 * sizeof(float) * cap);
+    d_depth_norm_.ensure(lr_px0 * sizeof(float) * cap);
+    cap_tiles_ = cap;
+    return;
+  }
   for (size_t i = 0; i < tensors_.size(); ++i) {
     if ((int)i == 0 || (int)i == 1 || (int)i == hdr_.out_tensor) continue;  // alias caller buffers
     const auto& t = tensors_[i];
@@ -125,7 +140,7 @@ void Engine::ensure_arena(int n_tiles) {
 }
 
 float* Engine::tptr(int tid, int sub_start) const {
-  if (tid < 0) return nullptr;
+  if (tid < 0 || !tbase_[tid]) return nullptr;
   const auto& t = tensors_[tid];
   float* base = tbase_[tid];
   if (big_[tid]) return base;
@@ -145,6 +160,9 @@ void Engine::run_ops(bool hr_phase, int n, int sub_start, cudaStream_t s) {
     const float* rs = tptr(op.res, sub_start);
     float* dst = tptr(op.dst, sub_start);
     const int c1 = op.src1 >= 0 ? tensors_[op.src1].c : 0;
+    const int cat = op.kind == FSR_OP_HEAD ? PROF_HEAD : op.kind == FSR_OP_CONVT ? PROF_CONVT
+                  : op.kind == FSR_OP_CONV ? PROF_LR_CONV : PROF_LR_MISC;
+    ProfScope scope(prof, cat, s);
     switch (op.kind) {
       case FSR_OP_CONV:
         launch_conv_fp32(s0, ts.c, s1, c1, wp(op.w_off), wp(op.b_off), rs, dst, n, td.h, td.w, op.k, op.cout, op.act, op.alpha, s);
@@ -173,7 +191,8 @@ void Engine::run_ops(bool hr_phase, int n, int sub_start, cudaStream_t s) {
   }
 }
 
-void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_norm, float* d_pred_norm, cudaStream_t s) {
+void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_norm, float* d_pred_norm, float* d_pred_m,
+                     float max_depth, float denom, cudaStream_t s) {
   if (n_tiles <= 0) return;
   const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile, lr_px = (size_t)hdr_.lr_tile * hdr_.lr_tile;
   for (int c0 = 0; c0 < n_tiles; c0 += chunk_tiles_) {
@@ -182,9 +201,22 @@ void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_
     for (size_t i = 0; i < tensors_.size(); ++i) tbase_[i] = tbuf_[i].as<float>();
     tbase_[0] = const_cast<float*>(d_depth_norm) + (size_t)c0 * lr_px;
     tbase_[1] = const_cast<float*>(d_dem_norm) + (size_t)c0 * hr_px;
-    tbase_[hdr_.out_tensor] = d_pred_norm + (size_t)c0 * hr_px;
+    float* pm = d_pred_m ? d_pred_m + (size_t)c0 * hr_px : nullptr;
+    if (precision_ == FSR_PREC_BF16) {
+      tbase_[hdr_.out_tensor] = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
+      tc_run_ops(false, n, 0, nullptr, max_depth, denom, s);
+      for (int sub = 0; sub < n; sub += hr_sub_) tc_run_ops(true, std::min(hr_sub_, n - sub), sub, pm, max_depth, denom, s);
+      continue;
+    }
+    // fp32 path always materialises the normalised prediction, then inverts it
+    float* pn = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : d_pred_norm_.as<float>();
+    tbase_[hdr_.out_tensor] = pn;
     run_ops(false, n, 0, s);
     for (int sub = 0; sub < n; sub += hr_sub_) run_ops(true, std::min(hr_sub_, n - sub), sub, s);
+    if (pm) {
+      ProfScope scope(prof, PROF_INVERT, s);
+      launch_invert_depth(pn, pm, (size_t)n * hr_px, max_depth, denom, s);
+    }
   }
 }
 
@@ -196,11 +228,13 @@ void Engine::run_tiles_from_grid(const float* d_depth, const float* d_dem, const
   for (int c0 = 0; c0 < n_tiles; c0 += chunk_tiles_) {
     const int n = std::min(chunk_tiles_, n_tiles - c0);
     ensure_arena(n);
-    launch_tile_normalize(d_dem, d_depth, grid, tile_base + c0, n, T, TL, hdr_.scale, p, d_dem_norm_.as<float>(),
-                          d_depth_norm_.as<float>(), d_stats_out, d_flags(), s);
-    float* pn = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : d_pred_norm_.as<float>();
-    forward(n, d_depth_norm_.as<float>(), d_dem_norm_.as<float>(), pn, s);
-    launch_invert_depth(pn, d_pred_m + (size_t)c0 * hr_px, (size_t)n * hr_px, p.max_depth, p.depth_denom, s);
+    {
+      ProfScope scope(prof, PROF_PROLOGUE, s);
+      launch_tile_normalize(d_dem, d_depth, grid, tile_base + c0, n, T, TL, hdr_.scale, p, d_dem_norm_.as<float>(),
+                            d_depth_norm_.as<float>(), d_stats_out, d_flags(), s);
+    }
+    float* pn = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
+    forward(n, d_depth_norm_.as<float>(), d_dem_norm_.as<float>(), pn, d_pred_m + (size_t)c0 * hr_px, p.max_depth, p.depth_denom, s);
   }
 }
 
@@ -344,12 +378,14 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
   e.band = BandState{ty0, ty1, row0, n_rows, halo_out, p.max_depth};
   if (halo_out > 0 && d_halo_out) {
     BlendGeom g = e.blend_geom();
+    ProfScope scope(e.prof, PROF_BLEND, s);
     launch_blend(e.d_tiles.as<float>(), ty0, ty1, g, row0 + n_rows, halo_out, nullptr, 0, false, p.max_depth, d_halo_out, s);
   }
 }
 
 static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s) {
   BlendGeom g = e.blend_geom();
+  ProfScope scope(e.prof, PROF_BLEND, s);
   launch_blend(e.d_tiles.as<float>(), e.band.ty0, e.band.ty1, g, e.band.row0, e.band.n_rows, d_halo_in, halo_rows_in, true,
                e.band.max_depth, d_out_rows, s);
 }
@@ -610,7 +646,7 @@ int fsr_stage_forward(fsr_engine* eng, const float* depth_norm, const float* dem
   e.d_out.ensure(hr_px * n_tiles * sizeof(float));
   FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_norm, lr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, dem_norm, hr_px * n_tiles * sizeof(float), cudaMemcpyHostToDevice, s));
-  e.forward(n_tiles, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), e.d_out.as<float>(), s);
+  e.forward(n_tiles, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), e.d_out.as<float>(), nullptr, 5.0f, 1.791759f, s);
   FSR_CUDA(cudaMemcpyAsync(out_pred_norm, e.d_out.p, hr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
   FSR_CUDA(cudaStreamSynchronize(s));
   FSR_API_END()
@@ -646,6 +682,46 @@ int fsr_stage_blend(fsr_engine* eng, const float* tiles, int32_t H, int32_t W, i
   launch_blend(e.d_tiles.as<float>(), 0, ny, g, 0, H, nullptr, 0, true, max_depth, e.d_out.as<float>(), s);
   FSR_CUDA(cudaMemcpyAsync(out_sr, e.d_out.p, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToHost, s));
   FSR_CUDA(cudaStreamSynchronize(s));
+  FSR_API_END()
+}
+
+int fsr_profile_enable(fsr_engine* eng, int32_t on) {
+  FSR_API_BEGIN(eng)
+  eng->impl.prof.reset();
+  eng->impl.prof.on = on != 0;
+  FSR_API_END()
+}
+
+int fsr_profile_fetch(fsr_engine* eng, double* out_ms, int64_t* out_count, int32_t n_cat) {
+  FSR_API_BEGIN(eng)
+  FSR_REQUIRE(out_ms && out_count && n_cat >= PROF_NCAT, "need room for all profile categories");
+  eng->impl.prof.collect();
+  for (int i = 0; i < PROF_NCAT; ++i) {
+    out_ms[i] = eng->impl.prof.ms[i];
+    out_count[i] = eng->impl.prof.count[i];
+  }
+  FSR_API_END()
+}
+
+int fsr_debug_tensor_shape(fsr_engine* eng, int32_t tensor, int32_t* h, int32_t* w, int32_t* c) {
+  FSR_API_BEGIN(eng)
+  FSR_REQUIRE(tensor >= 0 && tensor < eng->impl.n_tensors(), "tensor index out of range");
+  const fsr_tensor_desc d = eng->impl.tensor_desc(tensor);
+  if (h) *h = d.h;
+  if (w) *w = d.w;
+  if (c) *c = d.c;
+  FSR_API_END()
+}
+
+int fsr_debug_read_tensor(fsr_engine* eng, int32_t tensor, int32_t n_tiles, float* out) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  FSR_REQUIRE(tensor >= 0 && tensor < e.n_tensors() && n_tiles > 0 && out, "bad tensor index or buffer");
+  const fsr_tensor_desc d = e.tensor_desc(tensor);
+  const size_t n = (size_t)n_tiles * d.h * d.w * d.c;
+  e.d_tmp_b.ensure(n * sizeof(float));
+  e.debug_read_tensor(tensor, n_tiles, e.d_tmp_b.as<float>(), 0);
+  FSR_CUDA(cudaMemcpy(out, e.d_tmp_b.p, n * sizeof(float), cudaMemcpyDeviceToHost));
   FSR_API_END()
 }
 

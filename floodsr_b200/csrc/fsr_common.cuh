@@ -6,6 +6,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/floodsr_b200.h"
 #include "fsr_plan.h"
@@ -44,6 +45,66 @@ inline void count_launch() {
     ::fsr::count_launch();                 \
     FSR_CUDA(cudaGetLastError());          \
   } while (0)
+
+// Optional per-stage device timing (bench.py roofline): CUDA events bracket each launch group on the
+// launching stream; elapsed times are summed per category when fetched.
+enum ProfCat { PROF_PROLOGUE = 0, PROF_LR_CONV, PROF_LR_MISC, PROF_CONVT, PROF_HEAD, PROF_INVERT, PROF_BLEND, PROF_NCAT };
+struct Profiler {
+  bool on = false;
+  struct Rec {
+    int cat;
+    cudaEvent_t a, b;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[PROF_NCAT] = {0};
+  long long count[PROF_NCAT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    FSR_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  void collect() {
+    for (auto& r : recs) {
+      FSR_CUDA(cudaEventSynchronize(r.b));
+      float t = 0.f;
+      FSR_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+      ms[r.cat] += t;
+      count[r.cat] += 1;
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  void reset() {
+    collect();
+    for (int i = 0; i < PROF_NCAT; ++i) ms[i] = 0, count[i] = 0;
+  }
+  ~Profiler() {
+    for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+struct ProfScope {
+  Profiler* p;
+  cudaStream_t s;
+  size_t idx = 0;
+  ProfScope(Profiler& prof, int cat, cudaStream_t stream) : p(prof.on ? &prof : nullptr), s(stream) {
+    if (!p) return;
+    Profiler::Rec r{cat, p->get(), p->get()};
+    FSR_CUDA(cudaEventRecord(r.a, s));
+    p->recs.push_back(r);
+    idx = p->recs.size() - 1;
+  }
+  ~ProfScope() {
+    if (p) cudaEventRecord(p->recs[idx].b, s);
+  }
+};
 
 // Where one tile's pixels come from: a window of a (virtually zero-padded) raster.  A batch of B
 // independent tiles is the raster [B*T, T] with origins (t*T, 0).

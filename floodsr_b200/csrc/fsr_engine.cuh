@@ -81,6 +81,16 @@ struct BandState {
   float max_depth = 0.f;
 };
 
+// Per-op state of the bf16 tensor-core backend (fsr_tc_backend.cu).
+struct TcOp {
+  DeviceBuf wpack;         // bf16 weights in the streaming layout of the op's kernel
+  DeviceBuf packbuf;       // CP8 staging tensor for convs fed by 1-channel fp32 rasters
+  bool pack_small = false;
+  int kc = 0, C0 = 0, C1 = 0;
+  std::vector<float> h_wdem, h_bias, h_w2;  // head epilogue constants (passed as kernel parameters)
+  float h_b2 = 0.f;
+};
+
 class Engine {
  public:
   BandState band;
@@ -92,9 +102,15 @@ class Engine {
   int scale() const { return hdr_.scale; }
   int64_t macs_per_tile() const;
   LaunchCounter launches;
+  Profiler prof;
 
   // network forward on normalised inputs resident on the device: [n,lr,lr] + [n,hr,hr] -> [n,hr,hr]
-  void forward(int n_tiles, const float* d_depth_norm, const float* d_dem_norm, float* d_pred_norm, cudaStream_t s);
+  // d_pred_norm and/or d_pred_m (metres, a11 fused or applied right after) may be nullptr
+  void forward(int n_tiles, const float* d_depth_norm, const float* d_dem_norm, float* d_pred_norm, float* d_pred_m,
+               float max_depth, float denom, cudaStream_t s);
+  void debug_read_tensor(int tid, int n_tiles, float* d_out, cudaStream_t s);
+  int n_tensors() const { return (int)tensors_.size(); }
+  fsr_tensor_desc tensor_desc(int tid) const { return tensors_[tid]; }
 
   // a5-a11 for tiles described by `grid` origins [tile_base, tile_base+n): writes metres (and optionally
   // the raw normalised prediction) per tile, stats at d_stats[(tile_base+i)*3]
@@ -119,6 +135,14 @@ class Engine {
   void ensure_arena(int n_tiles);
   void run_ops(bool hr_phase, int n, int sub_start, cudaStream_t s);
   float* tptr(int tid, int sub_start) const;
+  // bf16 tensor-core backend (fsr_tc_backend.cu)
+  void tc_prepare(const float* host_weights);
+  void tc_ensure_arena(int cap);
+  long long tc_plane(int tid) const;
+  void tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  std::vector<char> tc_fmt_;     // 1: CP8 bf16, 0: NHWC fp32
+  std::vector<int> tc_cpad_;     // channels as stored
+  std::vector<TcOp> tc_ops_;
 
   fsr_plan_header hdr_{};
   std::vector<fsr_tensor_desc> tensors_;

@@ -1,0 +1,297 @@
+// FSR_PREC_BF16 backend of the Engine: tensor formats, weight packing and op dispatch onto the tcgen05 kernels.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "fsr_engine.cuh"
+
+namespace fsr {
+
+// launchers implemented in k_tc_conv.cu / k_tc_head.cu
+int conv_tc_bn(int cout);
+void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
+                    const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
+                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, cudaStream_t s);
+void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
+                       int chunks, cudaStream_t s);
+void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
+                     long long plane_in, long long plane_out, cudaStream_t s);
+void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
+                         long long plane_in, long long plane_out, cudaStream_t s);
+void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
+                        cudaStream_t s);
+void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, cudaStream_t s);
+void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bfloat16* wpack, const float* bias,
+                     __nv_bfloat16* dst, long long plane_out, int n_img, int Hin, int Win, int cin, int cout, int k, int act,
+                     float alpha, cudaStream_t s);
+void launch_head_tc(const __nv_bfloat16* feat, long long plane, const __nv_bfloat16* wpack, const float* wdem, const float* bias,
+                    const float* w2, const float* b2, const float* dem, float* pred_m, float* pred_norm, int n_img, int H, int W,
+                    int cin, int cmid, int ksz, int act, float alpha, float max_depth, float denom, cudaStream_t s);
+
+static inline uint16_t f2bf(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Decide per-tensor storage and pack every conv-like op's weights into the layouts the kernels stream.
+void Engine::tc_prepare(const float* w) {
+  const int nt = (int)tensors_.size();
+  tc_fmt_.assign(nt, 0);
+  tc_cpad_.assign(nt, 0);
+  for (int i = 0; i < nt; ++i) {
+    tc_fmt_[i] = tensors_[i].c >= 8 ? 1 : 0;  // 1: CP8 bf16, 0: NHWC fp32 (1-channel rasters)
+    tc_cpad_[i] = tc_fmt_[i] ? round_up(tensors_[i].c, 16) : tensors_[i].c;
+  }
+  tc_ops_.clear();
+  tc_ops_.resize(ops_.size());
+  for (size_t oi = 0; oi < ops_.size(); ++oi) {
+    const fsr_op& op = ops_[oi];
+    TcOp& t = tc_ops_[oi];
+    auto need_cp8 = [&](int id, const char* what) {
+      if (id >= 0 && !tc_fmt_[id]) throw Error(FSR_E_UNSUPPORTED, std::string("bf16 backend: ") + what + " needs a >= 8-channel tensor");
+    };
+    if (op.kind == FSR_OP_CONV) {
+      const bool s0_small = !tc_fmt_[op.src0];
+      const bool s1_small = op.src1 >= 0 && !tc_fmt_[op.src1];
+      int C0, C1;
+      if (s0_small && (op.src1 < 0 || s1_small)) {
+        t.pack_small = true;  // concat of 1-channel rasters -> one zero-padded 16-channel CP8 tensor
+        C0 = 16;
+        C1 = 0;
+        FSR_REQUIRE(tensors_[op.src0].c + (op.src1 >= 0 ? tensors_[op.src1].c : 0) <= 16, "packed input wider than 16 channels");
+      } else {
+        need_cp8(op.src0, "conv source");
+        need_cp8(op.src1, "conv source");
+        C0 = tc_cpad_[op.src0];
+        C1 = op.src1 >= 0 ? tc_cpad_[op.src1] : 0;
+      }
+      need_cp8(op.dst, "conv output");
+      need_cp8(op.res, "conv residual");
+      FSR_REQUIRE(op.cout % 32 == 0, "bf16 backend: conv output channels must be a multiple of 32");
+      int kc = std::gcd(C0 / 8, C1 ? C1 / 8 : C0 / 8);
+      while (kc > 8 || (kc % 2)) {
+        if (kc % 2) throw Error(FSR_E_UNSUPPORTED, "bf16 backend: conv input channels must be multiples of 16");
+        kc /= 2;
+      }
+      t.kc = kc;
+      t.C0 = C0;
+      t.C1 = C1;
+      const int BN = conv_tc_bn(op.cout);
+      const int n_tiles = ceil_div(op.cout, BN);
+      const int taps = op.k * op.k;
+      const int s0 = (C0 / 8) / kc, s1 = C1 ? (C1 / 8) / kc : 0;
+      const int real_c0 = t.pack_small ? tensors_[op.src0].c + (op.src1 >= 0 ? tensors_[op.src1].c : 0) : tensors_[op.src0].c;
+      const int real_c1 = t.pack_small ? 0 : (op.src1 >= 0 ? tensors_[op.src1].c : 0);
+      const int cin_real = real_c0 + real_c1;
+      std::vector<uint16_t> pk((size_t)n_tiles * taps * (s0 + s1) * kc * BN * 8, 0);
+      const float* wt = w + op.w_off;  // [tap][cin_real][cout]
+      size_t pos = 0;
+      for (int nt_i = 0; nt_i < n_tiles; ++nt_i)
+        for (int tap = 0; tap < taps; ++tap)
+          for (int st = 0; st < s0 + s1; ++st)
+            for (int j = 0; j < kc; ++j)
+              for (int n = 0; n < BN; ++n)
+                for (int e = 0; e < 8; ++e, ++pos) {
+                  const int co = nt_i * BN + n;
+                  int ci;  // index into the concatenated real input channels, -1 = padding
+                  if (st < s0) {
+                    const int c = (st * kc + j) * 8 + e;
+                    ci = c < real_c0 ? c : -1;
+                  } else {
+                    const int c = ((st - s0) * kc + j) * 8 + e;
+                    ci = c < real_c1 ? real_c0 + c : -1;
+                  }
+                  if (ci >= 0 && co < op.cout) pk[pos] = f2bf(wt[((size_t)tap * cin_real + ci) * op.cout + co]);
+                }
+      t.wpack.ensure(pk.size() * 2);
+      FSR_CUDA(cudaMemcpy(t.wpack.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else if (op.kind == FSR_OP_CONVT) {
+      need_cp8(op.src0, "convT source");
+      need_cp8(op.dst, "convT output");
+      const int cin = tc_cpad_[op.src0], cin_real = tensors_[op.src0].c, cout = op.cout, k = op.k;
+      FSR_REQUIRE(cin % 16 == 0 && cin <= 64 && cout % 8 == 0 && 256 % cout == 0 && k % (256 / cout) == 0,
+                  "bf16 backend: unsupported transposed-convolution shape");
+      const int kc = cin / 8;
+      const int n_tiles = k * k * cout / 256;
+      const int kx_per_tile = 256 / cout, tiles_per_ky = k / kx_per_tile;
+      std::vector<uint16_t> pk((size_t)n_tiles * kc * 256 * 8, 0);
+      const float* wt = w + op.w_off;  // [ky][kx][cin_real][cout]
+      size_t pos = 0;
+      for (int nt_i = 0; nt_i < n_tiles; ++nt_i) {
+        const int ky = nt_i / tiles_per_ky, kx0 = (nt_i % tiles_per_ky) * kx_per_tile;
+        for (int j = 0; j < kc; ++j)
+          for (int n = 0; n < 256; ++n)
+            for (int e = 0; e < 8; ++e, ++pos) {
+              const int kx = kx0 + n / cout, co = n % cout, ci = j * 8 + e;
+              if (ci < cin_real) pk[pos] = f2bf(wt[(((size_t)ky * k + kx) * cin_real + ci) * cout + co]);
+            }
+      }
+      t.wpack.ensure(pk.size() * 2);
+      FSR_CUDA(cudaMemcpy(t.wpack.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else if (op.kind == FSR_OP_HEAD) {
+      need_cp8(op.src0, "head feature source");
+      FSR_REQUIRE(op.src1 >= 0 && !tc_fmt_[op.src1] && tensors_[op.src1].c == 1, "bf16 backend: head needs a 1-channel second source");
+      const int cf = tensors_[op.src0].c, cmid = op.cout;
+      FSR_REQUIRE(cf == 32 && cmid == 32 && op.k == 3, "bf16 backend: head is specialised for 32 -> 32 channels, 3x3");
+      const int cin_real = cf + 1;
+      const float* wt = w + op.w_off;  // [ky][kx][cin_real][cmid]
+      const int N = 3 * cmid;
+      // [kx][k-slice j][plane (2)][n = ky*cmid + co][8]
+      std::vector<uint16_t> pk((size_t)3 * 2 * 2 * N * 8, 0);
+      size_t pos = 0;
+      for (int kx = 0; kx < 3; ++kx)
+        for (int j = 0; j < 2; ++j)
+          for (int pl = 0; pl < 2; ++pl)
+            for (int n = 0; n < N; ++n)
+              for (int e = 0; e < 8; ++e, ++pos) {
+                const int ky = n / cmid, co = n % cmid, ci = j * 16 + pl * 8 + e;
+                pk[pos] = f2bf(wt[(((size_t)ky * 3 + kx) * cin_real + ci) * cmid + co]);
+              }
+      t.wpack.ensure(pk.size() * 2);
+      FSR_CUDA(cudaMemcpy(t.wpack.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      t.h_wdem.resize(9 * cmid);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int co = 0; co < cmid; ++co) t.h_wdem[tap * cmid + co] = wt[((size_t)tap * cin_real + cf) * cmid + co];
+      t.h_bias.assign(cmid, 0.f);
+      if (op.b_off >= 0) std::copy(w + op.b_off, w + op.b_off + cmid, t.h_bias.begin());
+      t.h_w2.assign(w + op.w2_off, w + op.w2_off + cmid);
+      t.h_b2 = op.b2_off >= 0 ? w[op.b2_off] : 0.f;
+    } else if (op.kind == FSR_OP_POOL) {
+      if (tc_fmt_[op.src0] != tc_fmt_[op.dst]) throw Error(FSR_E_UNSUPPORTED, "bf16 backend: pooling changes tensor format");
+    } else {
+      need_cp8(op.src0, "layer source");
+      need_cp8(op.src1, "layer source");
+      need_cp8(op.dst, "layer output");
+    }
+  }
+}
+
+void Engine::tc_ensure_arena(int cap) {
+  for (size_t i = 0; i < tensors_.size(); ++i) {
+    if ((int)i == 0 || (int)i == 1 || (int)i == hdr_.out_tensor) continue;
+    const auto& t = tensors_[i];
+    const size_t tiles = big_[i] ? hr_sub_ : cap;
+    const size_t elt = tc_fmt_[i] ? 2 : 4;
+    tbuf_[i].ensure((size_t)t.h * t.w * tc_cpad_[i] * elt * tiles);
+  }
+  for (size_t oi = 0; oi < ops_.size(); ++oi)
+    if (tc_ops_[oi].pack_small) {
+      const auto& d = tensors_[ops_[oi].dst];
+      tc_ops_[oi].packbuf.ensure((size_t)d.h * d.w * 16 * 2 * cap);
+    }
+}
+
+// pixels per CP8 plane of tensor `tid` as allocated (capacity, not the live batch)
+long long Engine::tc_plane(int tid) const {
+  const auto& t = tensors_[tid];
+  return (long long)(big_[tid] ? hr_sub_ : cap_tiles_) * t.h * t.w;
+}
+
+void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
+  const float* W = d_weights_.as<float>();
+  auto wp = [&](int off) -> const float* { return off >= 0 ? W + off : nullptr; };
+  // element pointer of a tensor for the live sub-batch: CP8 planes keep their capacity stride, so the sub-batch
+  // offset is a pixel offset inside every plane
+  auto cp8 = [&](int tid) -> __nv_bfloat16* {
+    if (tid < 0) return nullptr;
+    const auto& t = tensors_[tid];
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(tbase_[tid]);
+    return big_[tid] ? base : base + (size_t)sub_start * t.h * t.w * 8;
+  };
+  auto f32 = [&](int tid) -> float* {
+    if (tid < 0 || !tbase_[tid]) return nullptr;
+    const auto& t = tensors_[tid];
+    return tbase_[tid] + (size_t)sub_start * t.h * t.w * t.c;
+  };
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    if ((op_hr_[i] != 0) != hr_phase) continue;
+    const fsr_op& op = ops_[i];
+    TcOp& tc = tc_ops_[i];
+    const auto& ts = tensors_[op.src0];
+    const auto& td = tensors_[op.dst];
+    const int cat = op.kind == FSR_OP_HEAD ? PROF_HEAD : op.kind == FSR_OP_CONVT ? PROF_CONVT
+                  : op.kind == FSR_OP_CONV ? PROF_LR_CONV : PROF_LR_MISC;
+    ProfScope scope(prof, cat, s);
+    switch (op.kind) {
+      case FSR_OP_CONV: {
+        const __nv_bfloat16* s0;
+        const __nv_bfloat16* s1 = nullptr;
+        long long pl0, pl1 = 0;
+        if (tc.pack_small) {
+          __nv_bfloat16* pb = tc.packbuf.as<__nv_bfloat16>() + (size_t)sub_start * td.h * td.w * 8;
+          const long long plane = (long long)cap_tiles_ * td.h * td.w;
+          launch_pack_small(f32(op.src0), ts.c, f32(op.src1), op.src1 >= 0 ? tensors_[op.src1].c : 0, pb, (long long)n * td.h * td.w,
+                            plane, 2, s);
+          s0 = pb;
+          pl0 = plane;
+        } else {
+          s0 = cp8(op.src0);
+          pl0 = tc_plane(op.src0);
+          if (op.src1 >= 0) {
+            s1 = cp8(op.src1);
+            pl1 = tc_plane(op.src1);
+          }
+        }
+        launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
+                       tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, s);
+        break;
+      }
+      case FSR_OP_POOL:
+        if (tc_fmt_[op.src0])
+          launch_pool_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, op.mode, tc_plane(op.src0),
+                          tc_plane(op.dst), s);
+        else
+          launch_pool_fp32(f32(op.src0), f32(op.dst), n, ts.h, ts.w, ts.c, op.k, op.mode, s);
+        break;
+      case FSR_OP_UPSAMPLE:
+        launch_upsample_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst), s);
+        break;
+      case FSR_OP_ELTWISE: {
+        // planes are strided by capacity: run plane by plane over the live pixels
+        const long long live = (long long)n * td.h * td.w;
+        for (int c8 = 0; c8 < tc_cpad_[op.dst] / 8; ++c8) {
+          const size_t o = (size_t)c8 * tc_plane(op.dst) * 8;
+          launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, s);
+        }
+        break;
+      }
+      case FSR_OP_CONVT:
+        launch_convt_tc(cp8(op.src0), tc_plane(op.src0), tc.wpack.as<__nv_bfloat16>(), wp(op.b_off), cp8(op.dst), tc_plane(op.dst), n,
+                        ts.h, ts.w, tc_cpad_[op.src0], op.cout, op.k, op.act, op.alpha, s);
+        break;
+      case FSR_OP_HEAD: {
+        float* pn = f32(op.dst);  // may be nullptr when the caller does not want the normalised prediction
+        float* pm = d_pred_m ? d_pred_m + (size_t)sub_start * td.h * td.w : nullptr;
+        if (!pm) {
+          // forward-only call: metres go to scratch
+          d_tmp_b.ensure((size_t)hr_sub_ * td.h * td.w * sizeof(float));
+          pm = d_tmp_b.as<float>();
+        }
+        launch_head_tc(cp8(op.src0), tc_plane(op.src0), tc.wpack.as<__nv_bfloat16>(), tc.h_wdem.data(), tc.h_bias.data(),
+                       tc.h_w2.data(), &tc.h_b2, f32(op.src1), pm, pn, n, td.h, td.w, ts.c, op.cout, op.k, op.act, op.alpha,
+                       max_depth, denom, s);
+        break;
+      }
+      default:
+        throw Error(FSR_E_UNSUPPORTED, "op kind not implemented in the bf16 backend");
+    }
+  }
+}
+
+void Engine::debug_read_tensor(int tid, int n_tiles, float* d_out, cudaStream_t s) {
+  FSR_REQUIRE(tid >= 0 && tid < (int)tensors_.size() && tbase_[tid], "tensor is not materialised");
+  const auto& t = tensors_[tid];
+  const long long n_pix = (long long)n_tiles * t.h * t.w;
+  if (precision_ == FSR_PREC_BF16 && tc_fmt_[tid]) {
+    launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(tbase_[tid]), d_out, n_pix, tc_plane(tid), t.c, s);
+  } else {
+    FSR_CUDA(cudaMemcpyAsync(d_out, tbase_[tid], (size_t)n_pix * t.c * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+}
+
+}  // namespace fsr

@@ -1,0 +1,428 @@
+// tcgen05 implicit-GEMM convolution for the low-resolution backbone (FSR_PREC_BF16) and the CP8 helper kernels.
+//
+// Replaces ONNX Runtime's Conv kernels behind `session.run` (floodsr/engine/ort.py:193) for the ResUNet
+// encoder/decoder layers.  GEMM view: M = 128 output pixels (a bw x bh x bn box of the batched NHW grid),
+// N = BN output channels, K = taps x input channels over concat(src0, src1).
+//
+//   warp 0   TMA producer: per (tap, K-stage) one 5-D tiled TMA load of the shifted activation box
+//            (out-of-bounds coordinates are zero-filled = 'same' padding) + one bulk copy of packed weights
+//   warp 1   MMA issuer: tcgen05.mma kind::f16, accumulators in TMEM (BN fp32 columns)
+//   warps 2-5 epilogue: tcgen05.ld -> +bias (+residual) -> activation -> bf16 -> 16-byte CP8 stores
+//
+// Activations live in "CP8" layout [C/8][N][H][W][8] bf16 (see tc_common.cuh), so both UMMA operands use the
+// no-swizzle K-major canonical layout and a tap is just a TMA coordinate offset.
+#include "fsr_engine.cuh"
+#include "tc_common.cuh"
+
+namespace fsr {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kConvThreads = 192;
+
+struct ConvTcParams {
+  int H, W, N;             // per-image extent and number of images in this launch
+  int bw, bh, bn;          // M-tile box (bw*bh*bn == 128)
+  int tiles_x, tiles_y;    // tiles per image row / column
+  int ksz;                 // 1 or 3
+  int kc;                  // 8-channel chunks per K-stage (even, <= 8)
+  int s0, s1;              // K-stages per tap coming from src0 / src1
+  int cout;                // real output channels (multiple of 8)
+  int act;
+  float alpha;
+  long long plane;         // pixels per CP8 plane of the output/residual tensors (N_capacity * H * W)
+  const __nv_bfloat16* wpack;  // [n_tile][tap][stage][kc][BN][8]
+  const float* bias;           // [cout] or nullptr
+  const __nv_bfloat16* res;    // CP8 residual or nullptr
+  __nv_bfloat16* out;          // CP8 output
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kABytesMax = 8 * 128 * 16;
+  constexpr int kBBytesMax = 8 * BN * 16;
+  uint8_t* smem_a = smem_raw;                                   // kStages x kABytesMax
+  uint8_t* smem_b = smem_raw + kStages * kABytesMax;            // kStages x kBBytesMax
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * kBBytesMax);
+  uint64_t* full = bars;                // [kStages]
+  uint64_t* empty = bars + kStages;     // [kStages]
+  uint64_t* accum_full = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.ksz * p.ksz;
+  const int stages_per_tap = p.s0 + p.s1;
+  const int n_iters = taps * stages_per_tap;
+  const uint32_t a_bytes = (uint32_t)p.kc * 128u * 16u;
+  const uint32_t b_bytes = (uint32_t)p.kc * BN * 16u;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int tn = t / p.tiles_y;
+  const int n_tile = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.s1 > 0) tma_prefetch_desc(&tmA1);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      mbar_init(accum_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int pad = p.ksz / 2;
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
+        for (int st = 0; st < stages_per_tap; ++st, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], a_bytes + b_bytes);
+          const bool second = st >= p.s0;
+          const CUtensorMap* tm = second ? &tmA1 : &tmA0;
+          const int chunk0 = (second ? st - p.s0 : st) * p.kc;
+          tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 0, tx * p.bw + dx, ty * p.bh + dy, tn * p.bn, chunk0);
+          const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)p.kc * BN * 8);
+          bulk_load_1d(smem_b + s * kBBytesMax, wsrc, b_bytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, BN);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + s * kABytesMax);
+        const uint32_t b_addr = smem_u32(smem_b + s * kBBytesMax);
+        for (int j = 0; j < p.kc / 2; ++j) {
+          // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
+          const uint64_t da = smem_desc_kmajor(a_addr + j * 2 * (128 * 16), 128 * 16, 128);
+          const uint64_t db = smem_desc_kmajor(b_addr + j * 2 * (BN * 16), BN * 16, 128);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(accum_full);
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int lx = m % p.bw;
+    const int ly = (m / p.bw) % p.bh;
+    const int ln = m / (p.bw * p.bh);
+    const int n_img = tn * p.bn + ln;
+    const bool valid = n_img < p.N;
+    const long long pix = ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 8; ++c) {
+      float v[8];
+      tmem_ld8(taddr + c * 8, v);
+      tmem_ld_wait();
+      const int co = n_tile * BN + c * 8;
+      if (valid && co < p.cout) {
+        const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
+        if (p.bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (p.res) {
+          float r[8];
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += r[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act, p.alpha);
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.out + off) = o;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---- CP8 helper kernels (memory-bound, 16-byte vectors) -----------------------------------------------------
+
+// concat of up to two 1-channel fp32 NHWC tensors -> CP8 bf16 with `chunks` 8-channel planes (zero padded)
+__global__ void pack_small_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
+                                  __nv_bfloat16* __restrict__ dst, long long n_pix, long long plane, int chunks) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * chunks; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % n_pix;
+    const int ch = (int)(i / n_pix);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = ch * 8 + k;
+      float x = 0.0f;
+      if (c < c0) x = __ldg(s0 + pix * c0 + c);
+      else if (c < c0 + c1) x = __ldg(s1 + pix * c1 + (c - c0));
+      v[k] = x;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + ((long long)ch * plane + pix) * 8) = o;
+  }
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// k x k pooling (stride k) on CP8: one thread per (chunk, output pixel)
+__global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
+                                int Hin, int Win, int k, int mode, long long plane_in, long long plane_out) {
+  const int Hout = Hin / k, Wout = Win / k;
+  const long long n_out = (long long)n_img * Hout * Wout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % n_out;
+    const int ch = (int)(i / n_out);
+    const int X = (int)(pix % Wout);
+    const long long t2 = pix / Wout;
+    const int Y = (int)(t2 % Hout);
+    const long long img = t2 / Hout;
+    const __nv_bfloat16* base = src + (long long)ch * plane_in * 8;
+    if (mode == 0) {
+      uint4 acc = __ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k) * Win + (long long)X * k) * 8));
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx)
+          acc = bf16x8_max(acc, __ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)));
+      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = acc;
+    } else {
+      float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+          float f[8];
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] += f[j];
+        }
+      const float inv = 1.0f / (float)(k * k);
+      uint4 o;
+      o.x = pack_bf16x2(s[0] * inv, s[1] * inv); o.y = pack_bf16x2(s[2] * inv, s[3] * inv);
+      o.z = pack_bf16x2(s[4] * inv, s[5] * inv); o.w = pack_bf16x2(s[6] * inv, s[7] * inv);
+      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = o;
+    }
+  }
+}
+
+__global__ void upsample_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
+                                    int Hin, int Win, int f, long long plane_in, long long plane_out) {
+  const int Hout = Hin * f, Wout = Win * f;
+  const long long n_out = (long long)n_img * Hout * Wout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % n_out;
+    const int ch = (int)(i / n_out);
+    const int X = (int)(pix % Wout);
+    const long long t2 = pix / Wout;
+    const int Y = (int)(t2 % Hout);
+    const long long img = t2 / Hout;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((long long)ch * plane_in + (img * Hin + Y / f) * Win + X / f) * 8));
+    *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = v;
+  }
+}
+
+__global__ void eltwise_cp8_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                   __nv_bfloat16* __restrict__ dst, long long n_vec, int act, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
+    if (b) {
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(b) + i), y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += y[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], act, alpha);
+    uint4 o;
+    o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]); o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+}
+
+// CP8 bf16 -> NHWC fp32 (debug / parity reads of intermediate tensors)
+__global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n_pix, long long plane, int C) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * C; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C;
+    const int c = (int)(i % C);
+    dst[i] = __bfloat162float(src[((long long)(c >> 3) * plane + pix) * 8 + (c & 7)]);
+  }
+}
+
+inline int grid_for(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 148 * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <int BN>
+size_t conv_smem_bytes() {
+  return (size_t)kStages * (8 * 128 * 16) + (size_t)kStages * (8 * BN * 16) + (2 * kStages + 1) * sizeof(uint64_t) + 16;
+}
+
+}  // namespace
+
+// ---- host-side: tensor maps and launchers ------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  FSR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+  if (!ptr || qres != cudaDriverEntryPointSuccess) throw Error(FSR_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// 5-D tensor map over a CP8 activation tensor: dims (8, W, H, N, C/8), element strides in bytes
+// (2, 16, W*16, H*W*16, plane*16); box (8, bw, bh, bn, kc); no swizzle; out-of-bounds elements read as zero.
+CUtensorMap make_cp8_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc) {
+  CUtensorMap m;
+  cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)chunks};
+  cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)plane * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)kc};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(FSR_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+void conv_tc_tile_box(int H, int W, int& bw, int& bh, int& bn) {
+  // 128 output pixels per M tile: as many whole rows / images as needed
+  bw = W < 128 ? W : 128;
+  bh = (128 / bw) < H ? (128 / bw) : H;
+  bn = 128 / (bw * bh);
+  if (bw * bh * bn != 128 || W % bw || H % bh) throw Error(FSR_E_UNSUPPORTED, "feature-map size does not tile into 128-pixel boxes");
+}
+
+int conv_tc_bn(int cout) { return cout >= 128 ? 128 : (cout >= 64 ? 64 : 32); }
+
+void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
+                    const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
+                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, cudaStream_t s) {
+  ConvTcParams p{};
+  p.H = H; p.W = W; p.N = n_img;
+  conv_tc_tile_box(H, W, p.bw, p.bh, p.bn);
+  p.tiles_x = W / p.bw;
+  p.tiles_y = H / p.bh;
+  p.ksz = ksz;
+  p.kc = kc;
+  p.s0 = (C0 / 8) / kc;
+  p.s1 = src1 ? (C1 / 8) / kc : 0;
+  p.cout = cout;
+  p.act = act;
+  p.alpha = alpha;
+  p.plane = plane_out;
+  p.wpack = wpack;
+  p.bias = bias;
+  p.res = res;
+  p.out = dst;
+  const int tiles_n = ceil_div(n_img, p.bn);
+  CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc);
+  CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc) : m0;
+  const int BN = conv_tc_bn(cout);
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)ceil_div(cout, BN));
+  if (BN == 128) {
+    static bool attr = false;
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<128>())); attr = true; }
+    conv_tc_kernel<128><<<grid, kConvThreads, conv_smem_bytes<128>(), s>>>(m0, m1, p);
+  } else if (BN == 64) {
+    static bool attr = false;
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<64>())); attr = true; }
+    conv_tc_kernel<64><<<grid, kConvThreads, conv_smem_bytes<64>(), s>>>(m0, m1, p);
+  } else {
+    static bool attr = false;
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<32>())); attr = true; }
+    conv_tc_kernel<32><<<grid, kConvThreads, conv_smem_bytes<32>(), s>>>(m0, m1, p);
+  }
+  FSR_LAUNCH_CHECK();
+}
+
+void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
+                       int chunks, cudaStream_t s) {
+  pack_small_kernel<<<grid_for(n_pix * chunks), 256, 0, s>>>(s0, c0, s1, c1, dst, n_pix, plane, chunks);
+  FSR_LAUNCH_CHECK();
+}
+
+void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
+                     long long plane_in, long long plane_out, cudaStream_t s) {
+  pool_cp8_kernel<<<grid_for((long long)n_img * (Hin / k) * (Win / k) * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, k, mode,
+                                                                                                plane_in, plane_out);
+  FSR_LAUNCH_CHECK();
+}
+
+void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
+                         long long plane_in, long long plane_out, cudaStream_t s) {
+  upsample_cp8_kernel<<<grid_for((long long)n_img * Hin * f * Win * f * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, f,
+                                                                                                plane_in, plane_out);
+  FSR_LAUNCH_CHECK();
+}
+
+void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
+                        cudaStream_t s) {
+  eltwise_cp8_kernel<<<grid_for(n_vec), 256, 0, s>>>(a, b, dst, n_vec, act, alpha);
+  FSR_LAUNCH_CHECK();
+}
+
+void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, cudaStream_t s) {
+  cp8_to_nhwc_kernel<<<grid_for(n_pix * C), 256, 0, s>>>(src, dst, n_pix, plane, C);
+  FSR_LAUNCH_CHECK();
+}
+
+}  // namespace fsr

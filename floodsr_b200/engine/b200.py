@@ -154,6 +154,27 @@ class EngineB200(EngineBase):
         """CUDA kernel launches issued by this engine so far."""
         return int(_lib.load_library().fsr_launch_count(self._handle)) if self._handle else 0
 
+    def profile(self, on: bool) -> None:
+        """Enable/disable (and reset) per-stage CUDA-event timing inside the engine."""
+        _lib.check(_lib.load_library().fsr_profile_enable(self._handle, 1 if on else 0))
+
+    def profile_fetch(self) -> dict[str, tuple[float, int]]:
+        """{stage: (device ms, launch groups)} since `profile(True)`."""
+        n = len(_lib.PROF_CATEGORIES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        _lib.check(_lib.load_library().fsr_profile_fetch(self._handle, ms, cnt, n))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.PROF_CATEGORIES)}
+
+    def debug_tensor(self, tensor: int, n_tiles: int = 1) -> np.ndarray:
+        """Intermediate activation `tensor` of the last forward pass as float32 [n_tiles, h, w, c]."""
+        lib = _lib.load_library()
+        h, w, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(lib.fsr_debug_tensor_shape(self._handle, tensor, C.byref(h), C.byref(w), C.byref(c)))
+        out = np.empty((n_tiles, h.value, w.value, c.value), dtype=np.float32)
+        _lib.check(lib.fsr_debug_read_tensor(self._handle, tensor, n_tiles, _lib.fptr(out)))
+        return out
+
     def macs_per_tile(self) -> int:
         assert self.lowered is not None
         return self.lowered.macs_per_tile()

@@ -163,6 +163,21 @@ int fsr_stage_blend(fsr_engine* eng, const float* tiles, int32_t H, int32_t W, i
                     int32_t overlap_hr, const int32_t* y_starts, int32_t ny, const int32_t* x_starts,
                     int32_t nx, const float* ramp, float max_depth, float* out_sr);
 
+/* ---- per-stage device timing (bench.py roofline) -------------------------------------------------------
+ * When enabled, CUDA events bracket every launch group on its stream; fsr_profile_fetch synchronises and
+ * returns, per category, the summed device time in ms and the number of groups since the last enable.
+ * Categories: 0 tile normalisation, 1 LR convs, 2 LR pool/upsample/eltwise, 3 transposed conv, 4 head conv,
+ * 5 log1p inversion, 6 blend. */
+#define FSR_PROF_NCAT 7
+int fsr_profile_enable(fsr_engine* eng, int32_t on);
+int fsr_profile_fetch(fsr_engine* eng, double* out_ms, int64_t* out_count, int32_t n_cat);
+
+/* ---- debugging: read an intermediate activation of the last forward pass as NHWC float32 ------------------
+ * (first n_tiles tiles of the last chunk; bf16 CP8 tensors are converted).  Used by layer-by-layer parity
+ * tests between the fp32 and bf16 backends. */
+int fsr_debug_tensor_shape(fsr_engine* eng, int32_t tensor, int32_t* h, int32_t* w, int32_t* c);
+int fsr_debug_read_tensor(fsr_engine* eng, int32_t tensor, int32_t n_tiles, float* out);
+
 /* Pinned host memory for callers that want full-speed H2D/D2H through the host entry points. */
 void* fsr_host_alloc(size_t bytes);
 void fsr_host_free(void* p);
