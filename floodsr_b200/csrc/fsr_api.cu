@@ -32,7 +32,7 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_REQUIRE(hdr_.lr_tile > 0 && hdr_.hr_tile == hdr_.lr_tile * hdr_.scale, "inconsistent tile geometry");
   FSR_REQUIRE(hdr_.hr_tile % 64 == 0, "hr tile must be a multiple of 64");
   FSR_REQUIRE(hdr_.out_tensor >= 2 && hdr_.out_tensor < hdr_.n_tensors, "bad output tensor");
-  FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_BF16, "unknown precision mode");
+  FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_BF16 || precision == FSR_PREC_FP16, "unknown precision mode");
 
   const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
   big_.assign(tensors_.size(), 0);
@@ -74,10 +74,11 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_CUDA(cudaMemset(d_flags_.p, 0, sizeof(unsigned)));
   tbuf_.resize(tensors_.size());
   tbase_.assign(tensors_.size(), nullptr);
-  if (precision_ == FSR_PREC_BF16) {
+  if (precision_ != FSR_PREC_FP32) {
     cudaDeviceProp prop;
     FSR_CUDA(cudaGetDeviceProperties(&prop, device_));
-    if (prop.major != 10) throw Error(FSR_E_UNSUPPORTED, "the bf16 backend needs an sm_100 (Blackwell) device: tcgen05/TMEM/TMA");
+    if (prop.major != 10) throw Error(FSR_E_UNSUPPORTED, "the tensor-core backends need an sm_100 (Blackwell) device: tcgen05/TMEM/TMA");
+    n_sms_ = prop.multiProcessorCount;
     chunk_tiles_ = 256;
     tc_prepare(weights);
   }
@@ -112,7 +113,7 @@ void Engine::ensure_arena(int n_tiles) {
   const int cap = std::max(n_tiles, chunk_tiles_);
   size_t headmid = 0;
   const size_t hr_px0 = (size_t)hdr_.hr_tile * hdr_.hr_tile, lr_px0 = (size_t)hdr_.lr_tile * hdr_.lr_tile;
-  if (precision_ == FSR_PREC_BF16) {
+  if (precision_ != FSR_PREC_FP32) {
     tc_ensure_arena(cap);
     d_dem_norm_.ensure(hr_px0 * sizeof(float) * cap);
     d_pred_norm_.ensure(hr_px0 * sizeof(float) * cap);
@@ -202,7 +203,7 @@ void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_
     tbase_[0] = const_cast<float*>(d_depth_norm) + (size_t)c0 * lr_px;
     tbase_[1] = const_cast<float*>(d_dem_norm) + (size_t)c0 * hr_px;
     float* pm = d_pred_m ? d_pred_m + (size_t)c0 * hr_px : nullptr;
-    if (precision_ == FSR_PREC_BF16) {
+    if (precision_ != FSR_PREC_FP32) {
       tbase_[hdr_.out_tensor] = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
       tc_run_ops(false, n, 0, nullptr, max_depth, denom, s);
       for (int sub = 0; sub < n; sub += hr_sub_) tc_run_ops(true, std::min(hr_sub_, n - sub), sub, pm, max_depth, denom, s);

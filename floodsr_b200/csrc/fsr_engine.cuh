@@ -149,7 +149,7 @@ class Engine {
   std::vector<fsr_op> ops_;
   std::vector<char> big_;        // tensor is an HR feature map (only allocated for hr_sub_ tiles)
   std::vector<char> op_hr_;      // op touches a big tensor
-  int device_ = 0, precision_ = 0;
+  int device_ = 0, precision_ = 0, n_sms_ = 148;
   int cap_tiles_ = 0;            // arena capacity (tiles per chunk)
   int hr_sub_ = 4;               // tiles per HR sub-chunk
   int chunk_tiles_ = 64;

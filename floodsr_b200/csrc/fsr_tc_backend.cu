@@ -1,5 +1,7 @@
 // FSR_PREC_BF16 backend of the Engine: tensor formats, weight packing and op dispatch onto the tcgen05 kernels.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <string.h>
 
 #include <algorithm>
 #include <numeric>
@@ -12,27 +14,35 @@ namespace fsr {
 int conv_tc_bn(int cout);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
-                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, cudaStream_t s);
+                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, cudaStream_t s);
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
-                       int chunks, cudaStream_t s);
+                       int chunks, int half, cudaStream_t s);
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, cudaStream_t s);
+                     long long plane_in, long long plane_out, int half, cudaStream_t s);
 void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
                          long long plane_in, long long plane_out, cudaStream_t s);
 void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
-                        cudaStream_t s);
-void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, cudaStream_t s);
+                        int half, cudaStream_t s);
+void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, int half, cudaStream_t s);
 void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bfloat16* wpack, const float* bias,
                      __nv_bfloat16* dst, long long plane_out, int n_img, int Hin, int Win, int cin, int cout, int k, int act,
-                     float alpha, cudaStream_t s);
-void launch_head_tc(const __nv_bfloat16* feat, long long plane, const __nv_bfloat16* wpack, const float* wdem, const float* bias,
-                    const float* w2, const float* b2, const float* dem, float* pred_m, float* pred_norm, int n_img, int H, int W,
-                    int cin, int cmid, int ksz, int act, float alpha, float max_depth, float denom, cudaStream_t s);
+                     float alpha, int half, cudaStream_t s);
+size_t head2_pack_elems();
+void head2_pack(const float* w, const float* bias, uint16_t* dst, uint16_t (*cvt)(float));
+void launch_head2_tc(const __nv_bfloat16* feat, long long plane, const __nv_bfloat16* wpack, const float* w2, const float* b2,
+                     const float* dem, float* pred_m, float* pred_norm, int n_img, int H, int W, int cin, int cmid, int ksz,
+                     int act, float alpha, float max_depth, float denom, int half, int n_sms, cudaStream_t s);
 
+static bool g_pack_half = false;  // 16-bit format used while packing weights (set by tc_prepare)
 static inline uint16_t f2bf(float f) {
-  __nv_bfloat16 h = __float2bfloat16_rn(f);
   uint16_t u;
-  memcpy(&u, &h, 2);
+  if (g_pack_half) {
+    __half h = __float2half_rn(f);
+    memcpy(&u, &h, 2);
+  } else {
+    __nv_bfloat16 h = __float2bfloat16_rn(f);
+    memcpy(&u, &h, 2);
+  }
   return u;
 }
 
@@ -40,6 +50,7 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Decide per-tensor storage and pack every conv-like op's weights into the layouts the kernels stream.
 void Engine::tc_prepare(const float* w) {
+  g_pack_half = precision_ == FSR_PREC_FP16;
   const int nt = (int)tensors_.size();
   tc_fmt_.assign(nt, 0);
   tc_cpad_.assign(nt, 0);
@@ -138,22 +149,12 @@ void Engine::tc_prepare(const float* w) {
       FSR_REQUIRE(op.src1 >= 0 && !tc_fmt_[op.src1] && tensors_[op.src1].c == 1, "bf16 backend: head needs a 1-channel second source");
       const int cf = tensors_[op.src0].c, cmid = op.cout;
       FSR_REQUIRE(cf == 32 && cmid == 32 && op.k == 3, "bf16 backend: head is specialised for 32 -> 32 channels, 3x3");
-      const int cin_real = cf + 1;
-      const float* wt = w + op.w_off;  // [ky][kx][cin_real][cmid]
-      const int N = 3 * cmid;
-      // [kx][k-slice j][plane (2)][n = ky*cmid + co][8]
-      std::vector<uint16_t> pk((size_t)3 * 2 * 2 * N * 8, 0);
-      size_t pos = 0;
-      for (int kx = 0; kx < 3; ++kx)
-        for (int j = 0; j < 2; ++j)
-          for (int pl = 0; pl < 2; ++pl)
-            for (int n = 0; n < N; ++n)
-              for (int e = 0; e < 8; ++e, ++pos) {
-                const int ky = n / cmid, co = n % cmid, ci = j * 16 + pl * 8 + e;
-                pk[pos] = f2bf(wt[(((size_t)ky * 3 + kx) * cin_real + ci) * cmid + co]);
-              }
+      const float* wt = w + op.w_off;  // [ky][kx][cf + 1][cmid]
+      std::vector<uint16_t> pk(head2_pack_elems(), 0);
+      head2_pack(wt, op.b_off >= 0 ? w + op.b_off : nullptr, pk.data(), f2bf);
       t.wpack.ensure(pk.size() * 2);
       FSR_CUDA(cudaMemcpy(t.wpack.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      const int cin_real = cf + 1;
       t.h_wdem.resize(9 * cmid);
       for (int tap = 0; tap < 9; ++tap)
         for (int co = 0; co < cmid; ++co) t.h_wdem[tap * cmid + co] = wt[((size_t)tap * cin_real + cf) * cmid + co];
@@ -194,6 +195,7 @@ long long Engine::tc_plane(int tid) const {
 
 void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
   const float* W = d_weights_.as<float>();
+  const int half = precision_ == FSR_PREC_FP16 ? 1 : 0;
   auto wp = [&](int off) -> const float* { return off >= 0 ? W + off : nullptr; };
   // element pointer of a tensor for the live sub-batch: CP8 planes keep their capacity stride, so the sub-batch
   // offset is a pixel offset inside every plane
@@ -226,7 +228,7 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
           __nv_bfloat16* pb = tc.packbuf.as<__nv_bfloat16>() + (size_t)sub_start * td.h * td.w * 8;
           const long long plane = (long long)cap_tiles_ * td.h * td.w;
           launch_pack_small(f32(op.src0), ts.c, f32(op.src1), op.src1 >= 0 ? tensors_[op.src1].c : 0, pb, (long long)n * td.h * td.w,
-                            plane, 2, s);
+                            plane, 2, half, s);
           s0 = pb;
           pl0 = plane;
         } else {
@@ -238,13 +240,13 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
           }
         }
         launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
-                       tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, s);
+                       tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, s);
         break;
       }
       case FSR_OP_POOL:
         if (tc_fmt_[op.src0])
           launch_pool_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, op.mode, tc_plane(op.src0),
-                          tc_plane(op.dst), s);
+                          tc_plane(op.dst), half, s);
         else
           launch_pool_fp32(f32(op.src0), f32(op.dst), n, ts.h, ts.w, ts.c, op.k, op.mode, s);
         break;
@@ -256,13 +258,13 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
         const long long live = (long long)n * td.h * td.w;
         for (int c8 = 0; c8 < tc_cpad_[op.dst] / 8; ++c8) {
           const size_t o = (size_t)c8 * tc_plane(op.dst) * 8;
-          launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, s);
+          launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, half, s);
         }
         break;
       }
       case FSR_OP_CONVT:
         launch_convt_tc(cp8(op.src0), tc_plane(op.src0), tc.wpack.as<__nv_bfloat16>(), wp(op.b_off), cp8(op.dst), tc_plane(op.dst), n,
-                        ts.h, ts.w, tc_cpad_[op.src0], op.cout, op.k, op.act, op.alpha, s);
+                        ts.h, ts.w, tc_cpad_[op.src0], op.cout, op.k, op.act, op.alpha, half, s);
         break;
       case FSR_OP_HEAD: {
         float* pn = f32(op.dst);  // may be nullptr when the caller does not want the normalised prediction
@@ -272,9 +274,8 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
           d_tmp_b.ensure((size_t)hr_sub_ * td.h * td.w * sizeof(float));
           pm = d_tmp_b.as<float>();
         }
-        launch_head_tc(cp8(op.src0), tc_plane(op.src0), tc.wpack.as<__nv_bfloat16>(), tc.h_wdem.data(), tc.h_bias.data(),
-                       tc.h_w2.data(), &tc.h_b2, f32(op.src1), pm, pn, n, td.h, td.w, ts.c, op.cout, op.k, op.act, op.alpha,
-                       max_depth, denom, s);
+        launch_head2_tc(cp8(op.src0), tc_plane(op.src0), tc.wpack.as<__nv_bfloat16>(), tc.h_w2.data(), &tc.h_b2, f32(op.src1), pm, pn,
+                        n, td.h, td.w, ts.c, op.cout, op.k, op.act, op.alpha, max_depth, denom, half, n_sms_, s);
         break;
       }
       default:
@@ -287,8 +288,8 @@ void Engine::debug_read_tensor(int tid, int n_tiles, float* d_out, cudaStream_t 
   FSR_REQUIRE(tid >= 0 && tid < (int)tensors_.size() && tbase_[tid], "tensor is not materialised");
   const auto& t = tensors_[tid];
   const long long n_pix = (long long)n_tiles * t.h * t.w;
-  if (precision_ == FSR_PREC_BF16 && tc_fmt_[tid]) {
-    launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(tbase_[tid]), d_out, n_pix, tc_plane(tid), t.c, s);
+  if (precision_ != FSR_PREC_FP32 && tc_fmt_[tid]) {
+    launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(tbase_[tid]), d_out, n_pix, tc_plane(tid), t.c, precision_ == FSR_PREC_FP16 ? 1 : 0, s);
   } else {
     FSR_CUDA(cudaMemcpyAsync(d_out, tbase_[tid], (size_t)n_pix * t.c * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }

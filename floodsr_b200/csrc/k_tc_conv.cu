@@ -33,6 +33,7 @@ struct ConvTcParams {
   int cout;                // real output channels (multiple of 8)
   int act;
   float alpha;
+  int half;                // 16-bit format: 0 bf16, 1 fp16
   long long plane;         // pixels per CP8 plane of the output/residual tensors (N_capacity * H * W)
   const __nv_bfloat16* wpack;  // [n_tile][tap][stage][kc][BN][8]
   const float* bias;           // [cout] or nullptr
@@ -113,25 +114,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(128, BN);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + s * kABytesMax);
-        const uint32_t b_addr = smem_u32(smem_b + s * kBBytesMax);
-        for (int j = 0; j < p.kc / 2; ++j) {
-          // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
-          const uint64_t da = smem_desc_kmajor(a_addr + j * 2 * (128 * 16), 128 * 16, 128);
-          const uint64_t db = smem_desc_kmajor(b_addr + j * 2 * (BN * 16), BN * 16, 128);
-          umma_bf16(tmem_base, da, db, idesc, (it > 0 || j > 0) ? 1u : 0u);
-        }
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc = idesc_16(128, BN, p.half);
+    const uint64_t da_base = smem_desc_kmajor(smem_u32(smem_a), 128 * 16, 128);
+    const uint64_t db_base = smem_desc_kmajor(smem_u32(smem_b), BN * 16, 128);
+    const int kpairs = p.kc / 2;
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint64_t da = da_base + (uint64_t)((s * kABytesMax) >> 4);
+      const uint64_t db = db_base + (uint64_t)((s * kBBytesMax) >> 4);
+      if (elect_one()) {
+        // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
+        for (int j = 0; j < kpairs; ++j)
+          umma_bf16(tmem_base, da + (uint64_t)((j * 2 * (128 * 16)) >> 4), db + (uint64_t)((j * 2 * (BN * 16)) >> 4), idesc,
+                    (it > 0 || j > 0) ? 1u : 0u);
         umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        if (it == n_iters - 1) umma_commit(accum_full);
       }
-      umma_commit(accum_full);
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -162,18 +165,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (p.res) {
           float r[8];
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), r);
+          unpack_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), r, p.half);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] += r[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act, p.alpha);
-        uint4 o;
-        o.x = pack_bf16x2(v[0], v[1]);
-        o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]);
-        o.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(p.out + off) = o;
+        *reinterpret_cast<uint4*>(p.out + off) = pack_x8(v, p.half);
       }
     }
     tc_fence_before();
@@ -189,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
 // concat of up to two 1-channel fp32 NHWC tensors -> CP8 bf16 with `chunks` 8-channel planes (zero padded)
 __global__ void pack_small_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
-                                  __nv_bfloat16* __restrict__ dst, long long n_pix, long long plane, int chunks) {
+                                  __nv_bfloat16* __restrict__ dst, long long n_pix, long long plane, int chunks, int half) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * chunks; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i % n_pix;
     const int ch = (int)(i / n_pix);
@@ -202,25 +200,31 @@ __global__ void pack_small_kernel(const float* __restrict__ s0, int c0, const fl
       else if (c < c0 + c1) x = __ldg(s1 + pix * c1 + (c - c0));
       v[k] = x;
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst + ((long long)ch * plane + pix) * 8) = o;
+    *reinterpret_cast<uint4*>(dst + ((long long)ch * plane + pix) * 8) = pack_x8(v, half);
   }
 }
 
-__device__ __forceinline__ uint4 bf16x8_max(const uint4& a, const uint4& b) {
+__device__ __forceinline__ uint4 x8_max(const uint4& a, const uint4& b, int half) {
   uint4 r;
-  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+  if (half) {
+    const __half2* pa = reinterpret_cast<const __half2*>(&a);
+    const __half2* pb = reinterpret_cast<const __half2*>(&b);
+    __half2* pr = reinterpret_cast<__half2*>(&r);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  } else {
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  }
   return r;
 }
 
 // k x k pooling (stride k) on CP8: one thread per (chunk, output pixel)
 __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
-                                int Hin, int Win, int k, int mode, long long plane_in, long long plane_out) {
+                                int Hin, int Win, int k, int mode, long long plane_in, long long plane_out, int half) {
   const int Hout = Hin / k, Wout = Win / k;
   const long long n_out = (long long)n_img * Hout * Wout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
@@ -235,22 +239,21 @@ __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bflo
       uint4 acc = __ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k) * Win + (long long)X * k) * 8));
       for (int dy = 0; dy < k; ++dy)
         for (int dx = 0; dx < k; ++dx)
-          acc = bf16x8_max(acc, __ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)));
+          acc = x8_max(acc, __ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)), half);
       *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = acc;
     } else {
       float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int dy = 0; dy < k; ++dy)
         for (int dx = 0; dx < k; ++dx) {
           float f[8];
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)), f);
+          unpack_x8(__ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)), f, half);
 #pragma unroll
           for (int j = 0; j < 8; ++j) s[j] += f[j];
         }
       const float inv = 1.0f / (float)(k * k);
-      uint4 o;
-      o.x = pack_bf16x2(s[0] * inv, s[1] * inv); o.y = pack_bf16x2(s[2] * inv, s[3] * inv);
-      o.z = pack_bf16x2(s[4] * inv, s[5] * inv); o.w = pack_bf16x2(s[6] * inv, s[7] * inv);
-      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] *= inv;
+      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = pack_x8(s, half);
     }
   }
 }
@@ -272,29 +275,29 @@ __global__ void upsample_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_
 }
 
 __global__ void eltwise_cp8_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                   __nv_bfloat16* __restrict__ dst, long long n_vec, int act, float alpha) {
+                                   __nv_bfloat16* __restrict__ dst, long long n_vec, int act, float alpha, int half) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
+    unpack_x8(__ldg(reinterpret_cast<const uint4*>(a) + i), x, half);
     if (b) {
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(b) + i), y);
+      unpack_x8(__ldg(reinterpret_cast<const uint4*>(b) + i), y, half);
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] += y[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], act, alpha);
-    uint4 o;
-    o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]); o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-    reinterpret_cast<uint4*>(dst)[i] = o;
+    reinterpret_cast<uint4*>(dst)[i] = pack_x8(x, half);
   }
 }
 
 // CP8 bf16 -> NHWC fp32 (debug / parity reads of intermediate tensors)
-__global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n_pix, long long plane, int C) {
+__global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n_pix, long long plane, int C,
+                                   int half) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * C; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / C;
     const int c = (int)(i % C);
-    dst[i] = __bfloat162float(src[((long long)(c >> 3) * plane + pix) * 8 + (c & 7)]);
+    const __nv_bfloat16* e = src + ((long long)(c >> 3) * plane + pix) * 8 + (c & 7);
+    dst[i] = half ? __half2float(*reinterpret_cast<const __half*>(e)) : __bfloat162float(*e);
   }
 }
 
@@ -343,6 +346,20 @@ CUtensorMap make_cp8_tensor_map(const void* base, int W, int H, int N, int chunk
   return m;
 }
 
+// 3-D tensor map over a 1-channel fp32 raster stack [N][H][W]: box (bw, 1, 1), zero fill outside.
+CUtensorMap make_f32_tensor_map_3d(const void* base, int W, int H, int N, int bw) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {(cuuint32_t)bw, 1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, N == 1 ? 2 : 3, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(FSR_E_CUDA, "cuTensorMapEncodeTiled (fp32 raster) failed with code " + std::to_string((int)r));
+  return m;
+}
+
 void conv_tc_tile_box(int H, int W, int& bw, int& bh, int& bn) {
   // 128 output pixels per M tile: as many whole rows / images as needed
   bw = W < 128 ? W : 128;
@@ -355,8 +372,9 @@ int conv_tc_bn(int cout) { return cout >= 128 ? 128 : (cout >= 64 ? 64 : 32); }
 
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
-                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, cudaStream_t s) {
+                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, cudaStream_t s) {
   ConvTcParams p{};
+  p.half = half;
   p.H = H; p.W = W; p.N = n_img;
   conv_tc_tile_box(H, W, p.bw, p.bh, p.bn);
   p.tiles_x = W / p.bw;
@@ -395,15 +413,15 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
 }
 
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
-                       int chunks, cudaStream_t s) {
-  pack_small_kernel<<<grid_for(n_pix * chunks), 256, 0, s>>>(s0, c0, s1, c1, dst, n_pix, plane, chunks);
+                       int chunks, int half, cudaStream_t s) {
+  pack_small_kernel<<<grid_for(n_pix * chunks), 256, 0, s>>>(s0, c0, s1, c1, dst, n_pix, plane, chunks, half);
   FSR_LAUNCH_CHECK();
 }
 
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, cudaStream_t s) {
+                     long long plane_in, long long plane_out, int half, cudaStream_t s) {
   pool_cp8_kernel<<<grid_for((long long)n_img * (Hin / k) * (Win / k) * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, k, mode,
-                                                                                                plane_in, plane_out);
+                                                                                                plane_in, plane_out, half);
   FSR_LAUNCH_CHECK();
 }
 
@@ -415,13 +433,13 @@ void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunk
 }
 
 void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
-                        cudaStream_t s) {
-  eltwise_cp8_kernel<<<grid_for(n_vec), 256, 0, s>>>(a, b, dst, n_vec, act, alpha);
+                        int half, cudaStream_t s) {
+  eltwise_cp8_kernel<<<grid_for(n_vec), 256, 0, s>>>(a, b, dst, n_vec, act, alpha, half);
   FSR_LAUNCH_CHECK();
 }
 
-void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, cudaStream_t s) {
-  cp8_to_nhwc_kernel<<<grid_for(n_pix * C), 256, 0, s>>>(src, dst, n_pix, plane, C);
+void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, int half, cudaStream_t s) {
+  cp8_to_nhwc_kernel<<<grid_for(n_pix * C), 256, 0, s>>>(src, dst, n_pix, plane, C, half);
   FSR_LAUNCH_CHECK();
 }
 

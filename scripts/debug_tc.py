@@ -12,7 +12,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 td = tempfile.mkdtemp()
 fp = write_h1_model(Path(td) / "model_infer.onnx", seed=0)
 e32 = EngineB200(fp, precision="fp32")
-e16 = EngineB200(fp, precision="bf16")
+e16 = EngineB200(fp, precision=sys.argv[2] if len(sys.argv) > 2 else "bf16")
 tiles = [synth_tile(s) for s in range(n)]
 depth = np.stack([t[0] for t in tiles]); dem = np.stack([t[1] for t in tiles])
 nrm = e32.stage_normalize(depth, dem)
