@@ -10,7 +10,7 @@ BASELINE config 5 (32k x 32k sharded in row bands, halo rows exchanged between n
 
 `value`   device-resident inputs/outputs, CUDA-event timed, max over ranks.
 `e2e`     same pass through the public API from pinned host buffers, H2D/D2H inside the timed region.
-`roofline` the dominant kernel (fused head conv) against the measured bf16 tensor peak.
+`roofline` the dominant kernel (fused head conv) against the measured bf16/fp16 dense tensor peak.
 `cpu_baseline` / `--impl reference`: the CPU oracle (torch-CPU restatement of the ONNX Runtime path; onnxruntime
 and the model asset are not available offline) on a bounded sample of the same workload, all host threads.
 """
@@ -117,6 +117,19 @@ class ClockSampler:
             "reasons": sorted(reasons),
             "samples": len(sm),
         }
+
+
+def head_traffic_per_launch(flops_per_launch: float):
+    """DRAM bytes (read + write) per launch of the head kernel from the committed ncu capture, scaled to this launch size."""
+    fp = REPO / "profiles" / "head_kernel_ncu.json"
+    if not fp.exists():
+        return None
+    rec = json.loads(fp.read_text())
+    try:
+        per_flop = (rec["dram_bytes_read"] + rec["dram_bytes_write"]) / rec["flops_per_launch"]
+        return per_flop * flops_per_launch
+    except (KeyError, ZeroDivisionError):
+        return None
 
 
 def cpu_reference_rate(model_fp: Path, sample_hw=(1024, 1536), steps: int = 1, warmup: int = 0) -> dict:
@@ -335,7 +348,7 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0)) if args.precision != "fp32" else float(peaks.get("bf16_tflops_sustained", 1400.0))
     roofline = {
         "bound": "tensor",
-        "kernel": "head_tc_kernel" if args.precision != "fp32" else "conv_igemm_fp32_kernel (head)",
+        "kernel": "head_tc_kernel (fused conv3x3+DEM+act+conv1x1+expm1, tcgen05)" if args.precision != "fp32" else "conv_igemm_fp32_kernel (head)",
         "achieved": achieved_tf,
         "peak": peak_tf,
         "unit": "TFLOP/s",
@@ -344,7 +357,7 @@ def main():
         "flops_per_launch": head_flops / max(head_launches, 1),
         "ms_per_launch": head_ms / max(head_launches, 1),
         "launches": head_launches,
-        "traffic": None,
+        "traffic": head_traffic_per_launch(head_flops / max(head_launches, 1)),
     }
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
     hbm_gbs = float(peaks.get("hbm_gbs", 6650.0))

@@ -1,4 +1,5 @@
 // C ABI (include/floodsr_b200.h) and the Engine that executes the lowered plan.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -80,6 +81,8 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
     if (prop.major != 10) throw Error(FSR_E_UNSUPPORTED, "the tensor-core backends need an sm_100 (Blackwell) device: tcgen05/TMEM/TMA");
     n_sms_ = prop.multiProcessorCount;
     chunk_tiles_ = 256;
+    hr_sub_ = 32;  // the HR feature map of a sub-chunk streams through HBM; long head launches amortise their prologue
+    if (const char* e = getenv("FSR_HR_SUB")) hr_sub_ = std::max(1, atoi(e));
     tc_prepare(weights);
   }
 }

@@ -151,7 +151,7 @@ class Engine {
   std::vector<char> op_hr_;      // op touches a big tensor
   int device_ = 0, precision_ = 0, n_sms_ = 148;
   int cap_tiles_ = 0;            // arena capacity (tiles per chunk)
-  int hr_sub_ = 4;               // tiles per HR sub-chunk
+  int hr_sub_ = 4;               // tiles per HR sub-chunk (tensor-core modes: 32; env FSR_HR_SUB overrides)
   int chunk_tiles_ = 64;
   DeviceBuf d_weights_, d_flags_, d_headmid_;
   std::vector<DeviceBuf> tbuf_;

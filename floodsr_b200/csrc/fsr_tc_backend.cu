@@ -28,7 +28,7 @@ void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bf
                      __nv_bfloat16* dst, long long plane_out, int n_img, int Hin, int Win, int cin, int cout, int k, int act,
                      float alpha, int half, cudaStream_t s);
 size_t head2_pack_elems();
-void head2_pack(const float* w, const float* bias, uint16_t* dst, uint16_t (*cvt)(float));
+void head2_pack(const float* w, const float* bias, uint16_t* dst, uint16_t (*cvt)(float), float (*back)(uint16_t));
 void launch_head2_tc(const __nv_bfloat16* feat, long long plane, const __nv_bfloat16* wpack, const float* w2, const float* b2,
                      const float* dem, float* pred_m, float* pred_norm, int n_img, int H, int W, int cin, int cmid, int ksz,
                      int act, float alpha, float max_depth, float denom, int half, int n_sms, cudaStream_t s);
@@ -44,6 +44,17 @@ static inline uint16_t f2bf(float f) {
     memcpy(&u, &h, 2);
   }
   return u;
+}
+
+static inline float bf2f(uint16_t u) {
+  if (g_pack_half) {
+    __half h;
+    memcpy(&h, &u, 2);
+    return __half2float(h);
+  }
+  __nv_bfloat16 h;
+  memcpy(&h, &u, 2);
+  return __bfloat162float(h);
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -125,7 +136,7 @@ void Engine::tc_prepare(const float* w) {
       need_cp8(op.src0, "convT source");
       need_cp8(op.dst, "convT output");
       const int cin = tc_cpad_[op.src0], cin_real = tensors_[op.src0].c, cout = op.cout, k = op.k;
-      FSR_REQUIRE(cin % 16 == 0 && cin <= 64 && cout % 8 == 0 && 256 % cout == 0 && k % (256 / cout) == 0,
+      FSR_REQUIRE(cin % 16 == 0 && cin <= 64 && cout == 32 && k % (256 / cout) == 0,
                   "bf16 backend: unsupported transposed-convolution shape");
       const int kc = cin / 8;
       const int n_tiles = k * k * cout / 256;
@@ -151,7 +162,7 @@ void Engine::tc_prepare(const float* w) {
       FSR_REQUIRE(cf == 32 && cmid == 32 && op.k == 3, "bf16 backend: head is specialised for 32 -> 32 channels, 3x3");
       const float* wt = w + op.w_off;  // [ky][kx][cf + 1][cmid]
       std::vector<uint16_t> pk(head2_pack_elems(), 0);
-      head2_pack(wt, op.b_off >= 0 ? w + op.b_off : nullptr, pk.data(), f2bf);
+      head2_pack(wt, op.b_off >= 0 ? w + op.b_off : nullptr, pk.data(), f2bf, bf2f);
       t.wpack.ensure(pk.size() * 2);
       FSR_CUDA(cudaMemcpy(t.wpack.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
       const int cin_real = cf + 1;

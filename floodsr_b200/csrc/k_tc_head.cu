@@ -133,6 +133,9 @@ convt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const ConvTParams p) {
       __syncwarp();
     }
   } else {
+    // epilogue: thread = one LR pixel; per (ky, 8-kx group) it owns 128 contiguous bytes in each 8-channel plane of
+    // the HR row, written as 256-bit stores (two adjacent kx per store: every 32-byte sector is written whole).
+    // Specialised for cout == 32 (one kx = 32 accumulator columns).
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int lx = m % p.bw;
@@ -144,7 +147,9 @@ convt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const ConvTParams p) {
     const int yin = ty * p.bh + ly, xin = tx * p.bw + lx;
     const int kx_per_tile = kCtBN / p.cout;
     const int tiles_per_ky = p.k / kx_per_tile;
-    const int cchunks = p.cout / 8;
+    float bias[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.0f;
     for (int i = 0; i < n_my; ++i) {
       const int s = i & 1;
       const int nt = nt0 + i;
@@ -155,23 +160,25 @@ convt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const ConvTParams p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * kCtBN;
       const long long row_pix = ((long long)n_img * Hout + (yin * p.k + ky)) * Wout + (long long)xin * p.k + kx0;
 #pragma unroll 1
-      for (int c8 = 0; c8 < cchunks; ++c8) {
-        float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8 + 4));
-          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-        }
-        __nv_bfloat16* dst = p.out + ((long long)c8 * p.plane_out + row_pix) * 8;
-#pragma unroll 1
-        for (int kx = 0; kx < kx_per_tile; ++kx) {
-          float v[8];
-          tmem_ld8(taddr + kx * p.cout + c8 * 8, v);
-          tmem_ld_wait();
-          if (valid) {
+      for (int kp = 0; kp < kCtBN / 64; ++kp) {
+        float v0[32], v1[32];
+        tmem_ld32(taddr + kp * 64, v0);
+        tmem_ld32(taddr + kp * 64 + 32, v1);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = apply_act(v[e] + b[e], p.act, p.alpha);
-            *reinterpret_cast<uint4*>(dst + (long long)kx * 8) = pack_x8(v, p.half);
+          for (int c8 = 0; c8 < 4; ++c8) {
+            float a[8], b[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              a[e] = apply_act(v0[c8 * 8 + e] + bias[c8 * 8 + e], p.act, p.alpha);
+              b[e] = apply_act(v1[c8 * 8 + e] + bias[c8 * 8 + e], p.act, p.alpha);
+            }
+            const uint4 lo = pack_x8(a, p.half), hi = pack_x8(b, p.half);
+            __nv_bfloat16* dst = p.out + ((long long)c8 * p.plane_out + row_pix + kp * 2) * 8;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+                         "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                         : "memory");
           }
         }
       }
@@ -197,7 +204,7 @@ void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bf
                      __nv_bfloat16* dst, long long plane_out, int n_img, int Hin, int Win, int cin, int cout, int k, int act,
                      float alpha, int half, cudaStream_t s) {
   FSR_REQUIRE(cin % 16 == 0 && cin <= 64, "convT tensor-core path needs cin in {16, 32, 48, 64}");
-  FSR_REQUIRE(cout % 8 == 0 && kCtBN % cout == 0 && k % (kCtBN / cout) == 0, "convT tensor-core path: unsupported cout / kernel size");
+  FSR_REQUIRE(cout == 32 && k % (kCtBN / cout) == 0, "convT tensor-core path is specialised for 32 output channels and kernel sizes that are multiples of 8");
   ConvTParams p{};
   p.half = half;
   p.Hin = Hin; p.Win = Win; p.N = n_img;

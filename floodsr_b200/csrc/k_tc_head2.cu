@@ -2,22 +2,27 @@
 // -> activation -> conv1x1 -> invert_depth_log1p.  ~81 % of the FLOPs behind `session.run`
 // (floodsr/engine/ort.py:193) plus the invert_depth_log1p_np call after it (ort.py:196, preprocessing.py:154-164).
 //
-// Persistent kernel, one CTA per SM, work item = 128-pixel-wide strip of RB output rows of one tile.
-// For every *input* row r of a strip one TMEM accumulator slot D'_r[x, (ky, co)] (N = 3*32 = 96 columns) is
-// produced from that row alone:
-//     D'_r[x, (ky, co)] = sum_{kx, ci} F[r, x + kx - 1, ci] * W[ky, kx, ci, co]          (6 MMAs, K = 3 x 32)
-//                       + sum_{kx}     dem[r, x + kx - 1]   * Wdem[ky, kx, co]  (+ bias) (1 MMA,  K = 16)
-// The kx taps are start-address offsets into the row's halo buffer (no-swizzle CP8 operand: 16 B per pixel per
-// 8-channel plane), so each feature row is fetched once (TMA, zero-filled outside the tile = 'same' padding).
-// The 1-channel DEM operand is built in shared memory by a dedicated warp as (hi, lo) 16-bit pairs, so the DEM
-// term keeps ~fp32 input precision; its K slot 6 is a constant 1 that carries the bias.
-// An output row then only needs same-lane TMEM reads:
-//     conv[y, x, co] = D'_{y-1}[x, (0, co)] + D'_y[x, (1, co)] + D'_{y+1}[x, (2, co)]
-// (carried as register partials so every slot is read once) followed by activation, the 1x1 projection, the log1p inversion and coalesced fp32 stores.
-// Operand traffic per FLOP is ~2x lower than a direct N = 32 formulation (A tiles are shared by 96 columns).
+// Persistent kernel, one CTA per SM.  The launch's output rows (128-pixel-wide strips of every tile, flattened)
+// are split into gridDim.x equal contiguous ranges, so every SM gets the same number of rows; a range is walked
+// as "items" = runs of rows inside one strip.
 //
-// Warp roles (256 threads): 0 TMA producer | 1 MMA issuer | 2 DEM prefetcher | 3 DEM-operand builder | 4-7 epilogue.
-// All hand-offs are mbarriers; accumulator slots form a ring of 5, each read once by the epilogue.
+// TMEM holds a ring of 16 output-row accumulators D_y[x, co] (128 lanes x 32 fp32 columns each = all 512
+// columns).  An *input* row r feeds the three output rows y = r+1, r, r-1 (ky = 0, 1, 2) with ONE N = 96 MMA per
+// K step, because their accumulators are adjacent in the ring and the weight operand is stored
+// [ky = 2 | ky = 1 | ky = 0] along N:
+//     D_{r-1} | D_r | D_{r+1}  +=  F[r, x + kx - 1, ci-slice] * [W(2,kx) | W(1,kx) | W(0,kx)]     (6 K steps)
+//                              +=  demop[r, x]                * [Wd(2)   | Wd(1)   | Wd(0)]       (1 K step)
+// The kx taps are start-address offsets into the row's halo buffer (no-swizzle CP8 operand: 16 B per pixel per
+// 8-channel plane), so each feature row is fetched once (TMA, zero-filled outside the tile = 'same' padding) and
+// the 3x3 sum happens inside the tensor core's fp32 accumulators.  Every MMA accumulates: the epilogue re-zeroes an
+// accumulator (tcgen05.st) right after reading it; ring wrap-around splits a row's MMAs in two.
+// The 1-channel DEM operand is built in shared memory by a dedicated warp as (hi, lo) 16-bit pairs so the DEM
+// term keeps ~fp32 input precision; its K slots 6/7 are constant 1 and carry the bias as a (hi, lo) pair.
+// When input row y+1 has been issued, D_y is complete: the epilogue reads its 32 columns once, applies the
+// activation, the 1x1 projection and the log1p inversion in fp32 and stores coalesced rows.
+//
+// Warp roles: 0 TMA producer | 1 MMA issuer | 2 DEM prefetcher | 3 DEM-operand builder | 4.. epilogue groups
+// (4 warps each, output rows alternate between groups).  All hand-offs are mbarriers.
 #include <stdlib.h>
 
 #include "fsr_engine.cuh"
@@ -28,29 +33,28 @@ namespace fsr {
 using namespace tc;
 
 CUtensorMap make_cp8_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc);
-CUtensorMap make_f32_tensor_map_3d(const void* base, int W, int H, int N, int bw);
 
 namespace {
 
 constexpr int kCmid = 32;
-constexpr int kN = 3 * kCmid;                     // accumulator columns per slot
-constexpr int kSlots = 5;
+constexpr int kNfull = 3 * kCmid;                 // widest MMA: three adjacent output-row accumulators
+constexpr int kSlots = 16;                        // 16 x 32 fp32 columns = the whole TMEM
 constexpr int kStages = 8;
 constexpr int kRowPx = 130;                       // 128 + left/right halo pixel
 constexpr int kPlaneBytes = kRowPx * 16;          // 2080
 constexpr int kRowBytes = 4 * kPlaneBytes;        // 32 feature channels = 4 planes
-constexpr int kWBytes = 3 * 2 * (2 * kN * 16);    // (kx, k-slice) x [2 planes][96][8]
-constexpr int kW2Bytes = 2 * kN * 16;             // DEM/bias operand [2 planes][96][8]
+constexpr int kWStep = 2 * kNfull * 16;           // one K step of the weight operand: [2 planes][96][8]
+constexpr int kWBytes = 6 * kWStep;               // (kx, k-slice)
+constexpr int kW2Bytes = kWStep;                  // DEM/bias operand
 constexpr int kA2Bytes = 128 * 16;                // DEM operand plane per stage
-constexpr int kDemBytes = 640;                    // per-stage staging (128-byte aligned)
-constexpr int kThreads = 256;
+constexpr int kDemBytes = 640;                    // per-stage fp32 DEM halo row (128-byte aligned)
+constexpr int kEpiGroups = 2;
+constexpr int kThreads = 128 + 128 * kEpiGroups;
 constexpr int kSmemBytes = 160 * 1024;            // > half an SM's shared memory: exactly one CTA per SM (TMEM is exclusive)
 
-struct Head2Params {
+struct HeadParams {
   int H, W, N;          // HR tile extent and tiles in this launch
-  int rb;               // output rows per work item
-  int n_items;
-  int act;
+  long long total_rows; // N * (W / 128) * H strip rows
   float alpha;
   int half;             // 16-bit format: 0 bf16, 1 fp16
   float max_depth, denom;
@@ -60,30 +64,42 @@ struct Head2Params {
   float* pred_norm;     // [N][H][W] or nullptr
   float w2[kCmid];      // 1x1 projection
   float b2;
-  int mode;             // debug switches
-  long long* stats;     // [16] per-role wait cycles of CTA 0 (debug)
-  unsigned* dbg;        // mapped host word: which wait timed out (debug builds of the pipeline)
+  long long* stats;     // optional [16] wait-cycle counters of CTA 0 (FSR_HEAD_STATS=1)
 };
 
-#define TWAIT(cnt, ...)                  \
-  do {                                    \
-    long long _t0 = clock64();            \
-    wait_tag(__VA_ARGS__);                \
-    cnt += clock64() - _t0;               \
-  } while (0)
-
-__device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, unsigned* dbg, unsigned tag) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (dbg) {
-        atomicCAS(dbg, 0u, tag);
-        __threadfence_system();
-      }
-      __trap();
-    }
+// mbarrier wait that adds the cycles spent to `cnt` (pipeline diagnostics; `cnt` is dead code when unused)
+template <bool STATS>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& cnt) {
+  if (STATS) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    cnt += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
   }
 }
+
+// Walks the items of this CTA's row range; every warp role iterates the same sequence.
+struct ItemIter {
+  long long r, r_end;
+  int H, segs;
+  int img, xs, y0, rows;
+  __device__ ItemIter(const HeadParams& p) : H(p.H), segs(p.W / 128) {
+    r = p.total_rows * (long long)blockIdx.x / gridDim.x;
+    r_end = p.total_rows * (long long)(blockIdx.x + 1) / gridDim.x;
+  }
+  __device__ bool next() {
+    if (r >= r_end) return false;
+    const long long strip = r / H;
+    y0 = (int)(r - strip * H);
+    const long long left = r_end - r;
+    rows = (H - y0) < left ? (H - y0) : (int)left;
+    img = (int)(strip / segs);
+    xs = (int)(strip % segs);
+    r += rows;
+    return true;
+  }
+};
 
 __device__ __forceinline__ uint16_t to16(float v, int half) {
   if (half) return __half_as_ushort(__float2half_rn(v));
@@ -94,33 +110,64 @@ __device__ __forceinline__ float from16(uint16_t u, int half) {
   return __bfloat162float(__ushort_as_bfloat16(u));
 }
 
+// Accumulating MMA with the 64-bit shared-memory descriptors given as 32-bit halves, so the issuing warp only does
+// 32-bit adds per instruction (descriptor layout: tc_common.cuh, smem_desc_kmajor).
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 da, db;\n"
+      ".reg .pred p;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.eq.u32 p, %4, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+// 32 lanes x 32 columns of zeros -> TMEM (re-arms an accumulator so that every MMA can accumulate)
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v, float alpha) {
+  if (ACT == FSR_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == FSR_ACT_LEAKY) return v > 0.0f ? v : v * alpha;
+  return v;
+}
+
+template <int ACT, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
-head2_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ Head2Params p) {
+head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ HeadParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem_w = smem_raw;                                   // 18432 B
   uint8_t* smem_w2 = smem_w + kWBytes;                          // 3072 B
   uint8_t* smem_rows = smem_w2 + kW2Bytes;                      // kStages x 8320 B (128-B aligned)
   uint8_t* smem_a2 = smem_rows + kStages * kRowBytes;           // kStages x 2048 B
-  uint8_t* smem_zero = smem_a2 + kStages * kA2Bytes;            // 2048 B of zeros (upper K plane of the DEM operand)
-  uint8_t* smem_dem = smem_zero + kA2Bytes;                     // kStages x 640 B fp32 DEM halo rows
+  uint8_t* smem_zero = smem_a2 + kStages * kA2Bytes;            // kStages x 2048 B of zeros: upper K plane of the DEM operand,
+                                                                // one per stage so the plane stride (LBO) is a constant
+  uint8_t* smem_dem = smem_zero + kStages * kA2Bytes;           // kStages x 640 B fp32 DEM halo rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dem + kStages * kDemBytes);
   uint64_t* w_full = bars;
   uint64_t* row_full = bars + 1;                 // [kStages]  TMA -> MMA
   uint64_t* a2_full = row_full + kStages;        // [kStages]  DEM builder -> MMA
   uint64_t* row_empty = a2_full + kStages;       // [kStages]  MMA -> producers
-  uint64_t* slot_full = row_empty + kStages;     // [kSlots]   MMA -> epilogue
-  uint64_t* slot_empty = slot_full + kSlots;     // [kSlots]   epilogue -> MMA (12 arrivals: 3 reading rows x 4 warps)
-  uint64_t* dem_full = slot_empty + kSlots;      // [kStages]  DEM prefetcher (32 cp.async arrivals) -> builder
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dem_full + kStages);
+  uint64_t* dem_full = row_empty + kStages;      // [kStages]  DEM prefetcher (32 cp.async arrivals) -> builder
+  uint64_t* slot_full = dem_full + kStages;      // [kSlots]   MMA -> epilogue
+  uint64_t* slot_empty = slot_full + kSlots;     // [kSlots]   epilogue (4 warps) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + kSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int segs = p.W / 128;
-  const int rblocks = p.H / p.rb;
-  const int n_in = p.rb + 2;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmF);
-  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmF);
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(w_full, 1);
@@ -141,13 +188,21 @@ head2_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     tmem_relinquish();
   }
   if (warp == 2) {
-    for (int i = lane; i < kA2Bytes / 16; i += 32) reinterpret_cast<uint4*>(smem_zero)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < kStages * kA2Bytes / 16; i += 32) reinterpret_cast<uint4*>(smem_zero)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 4 && warp < 8) {
+    // every MMA accumulates: start from zeroed accumulators (the epilogue re-zeroes a slot after reading it)
+    for (int sl = 0; sl < kSlots; ++sl) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + sl * kCmid);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one halo row per input row ===================
@@ -155,91 +210,100 @@ head2_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
       mbar_expect_tx(w_full, kWBytes + kW2Bytes);
       bulk_load_1d(smem_w, p.wpack, kWBytes + kW2Bytes, w_full);
       int g = 0;  // running input-row counter of this CTA
-      long long c_w0 = 0, c_t0 = clock64();
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        int t = item;
-        const int xs = t % segs;
-        t /= segs;
-        const int rbk = t % rblocks;
-        const int img = t / rblocks;
+      long long c0 = 0, t0 = STATS ? clock64() : 0;
+      for (ItemIter it(p); it.next();) {
+        const int n_in = it.rows + 2;
         for (int i = 0; i < n_in; ++i, ++g) {
           const int s = g % kStages;
-          TWAIT(c_w0, &row_empty[s], ((g / kStages) & 1) ^ 1, p.dbg, 0x100000u | g);
-          if (p.mode & 4) {
-            mbar_arrive(&row_full[s]);
-          } else {
-            mbar_expect_tx(&row_full[s], kRowBytes);
-            tma_load_5d(smem_rows + s * kRowBytes, &tmF, &row_full[s], 0, xs * 128 - 1, rbk * p.rb - 1 + i, img, 0);
-          }
+          mbar_wait_t<STATS>(&row_empty[s], ((g / kStages) & 1) ^ 1, c0);
+          mbar_expect_tx(&row_full[s], kRowBytes);
+          tma_load_5d(smem_rows + s * kRowBytes, &tmF, &row_full[s], 0, it.xs * 128 - 1, it.y0 - 1 + i, it.img, 0);
         }
       }
-      if (p.stats && blockIdx.x == 0) { p.stats[0] = c_w0; p.stats[1] = clock64() - c_t0; p.stats[15] = g; }
+      if (STATS && p.stats && blockIdx.x == 0) { p.stats[0] = c0; p.stats[1] = clock64() - t0; p.stats[2] = g; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: 6 feature MMAs + 1 DEM/bias MMA (N = 96) per input row ============
-    // The loop is warp-uniform (all lanes wait, one elected lane issues) and every descriptor is a precomputed
-    // base plus a 16-byte-unit offset: a divergent single-lane loop that rebuilds descriptors costs ~130
-    // cycles per MMA, more than twice the MMA itself (56 cycles at N = 96).
-    const uint32_t idesc = idesc_16(128, kN, p.half);
-    wait_tag(w_full, 0, p.dbg, 0x200000u);
-    uint64_t db[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) db[k] = smem_desc_kmajor(smem_u32(smem_w) + k * (2 * kN * 16), kN * 16, 128);
-    const uint64_t db2 = smem_desc_kmajor(smem_u32(smem_w2), kN * 16, 128);
-    const uint64_t da_base = smem_desc_kmajor(smem_u32(smem_rows), kPlaneBytes, 128);
-    const uint32_t zero_addr = smem_u32(smem_zero);
-    const uint32_t a2_base = smem_u32(smem_a2);
-    long long c_m0 = 0, c_m1 = 0, c_m2 = 0, c_mt = clock64();
-    int g = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      for (int i = 0; i < n_in; ++i, ++g) {
-        const int s = g % kStages;
-        const int slot = g % kSlots;
-        TWAIT(c_m0, &slot_empty[slot], ((g / kSlots) & 1) ^ 1, p.dbg, 0x300000u | g);
-        TWAIT(c_m1, &row_full[s], (g / kStages) & 1, p.dbg, 0x400000u | g);
-        if (!(p.mode & 1)) TWAIT(c_m2, &a2_full[s], (g / kStages) & 1, p.dbg, 0x500000u | g);
+    // ===================== MMA issuer =====================================================================
+    // One warp feeds the tensor core, so its instruction count per row is what limits the kernel once the epilogue
+    // is light: the loop is warp-uniform, descriptors are 32-bit bases plus immediates, ring indices and barrier
+    // phases are carried incrementally, and only the tcgen05 instructions themselves are issued by one lane.
+    const uint32_t idesc0 = idesc_16(128, 0, p.half);  // + (N >> 3) << 17 with N = 32 * accumulators
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+    mbar_wait(w_full, 0);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_w), kNfull * 16);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_rows), kPlaneBytes);
+    const uint32_t a2_lo0 = desc_lo(smem_u32(smem_a2), kStages * kA2Bytes);
+    const uint32_t bar_row_full = smem_u32(row_full), bar_a2_full = smem_u32(a2_full), bar_row_empty = smem_u32(row_empty);
+    const uint32_t bar_slot_full = smem_u32(slot_full);
+    const bool leader = elect_one();
+    int s = 0;            // smem stage of the current input row
+    uint32_t sph = 0;     // its barrier phase
+    int go = 0;           // output rows of earlier items
+    long long c_se = 0, c_rf = 0, c_af = 0, t0 = STATS ? clock64() : 0;
+    for (ItemIter it(p); it.next(); go += it.rows) {
+      const int n_in = it.rows + 2;
+      for (int i = 0; i < n_in; ++i) {
+        if (i < it.rows)  // output row i gets its first contribution (ky = 0) from this input row: its slot must be free
+          mbar_wait_t<STATS>(&slot_empty[(go + i) & (kSlots - 1)], (((go + i) / kSlots) & 1) ^ 1, c_se);
+        mbar_wait_t<STATS>(&row_full[s], sph, c_rf);
+        mbar_wait_t<STATS>(&a2_full[s], sph, c_af);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + slot * kN;
-        const uint64_t da_row = da_base + (uint64_t)((s * kRowBytes) >> 4);
-        const uint32_t a2_addr = a2_base + s * kA2Bytes;
-        const uint64_t da2 = smem_desc_kmajor(a2_addr, zero_addr - a2_addr, 128);
-        if (elect_one()) {
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            if (p.mode & 64) break;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              umma_bf16(d_addr, da_row + (uint64_t)((j * 2 * kPlaneBytes + kx * 16) >> 4), db[kx * 2 + j], idesc, (kx | j) ? 1u : 0u);
+        // output rows [jlo, jhi] accumulate from this input row; their slots are adjacent unless the ring wraps
+        const int jlo = i - 2 > 0 ? i - 2 : 0;
+        const int jhi = i < it.rows - 1 ? i : it.rows - 1;
+        const int n = jhi - jlo + 1;
+        const int sa = (go + jlo) & (kSlots - 1);
+        const int n1 = n < kSlots - sa ? n : kSlots - sa;
+        const uint32_t d1 = tmem_base + sa * kCmid;
+        const uint32_t id1 = idesc0 + ((uint32_t)n1 << 19);
+        const uint32_t b1 = b_lo0 + (uint32_t)(jlo - (i - 2)) * kCmid;  // weight rows (16 B each) of ky = i - jlo first
+        const uint32_t a = a_lo0 + s * (kRowBytes >> 4);
+        const uint32_t a2 = a2_lo0 + s * (kA2Bytes >> 4);
+        constexpr uint32_t kB = kWStep >> 4, kP = (2 * kPlaneBytes) >> 4;
+        if (leader) {
+          umma_acc(d1, a, b1, desc_hi, id1);
+          umma_acc(d1, a + kP, b1 + kB, desc_hi, id1);
+          umma_acc(d1, a + 1, b1 + 2 * kB, desc_hi, id1);
+          umma_acc(d1, a + kP + 1, b1 + 3 * kB, desc_hi, id1);
+          umma_acc(d1, a + 2, b1 + 4 * kB, desc_hi, id1);
+          umma_acc(d1, a + kP + 2, b1 + 5 * kB, desc_hi, id1);
+          umma_acc(d1, a2, b1 + 6 * kB, desc_hi, id1);
+          if (n1 < n) {
+            const uint32_t id2 = idesc0 + ((uint32_t)(n - n1) << 19);
+            const uint32_t b2 = b1 + n1 * kCmid;
+            umma_acc(tmem_base, a, b2, desc_hi, id2);
+            umma_acc(tmem_base, a + kP, b2 + kB, desc_hi, id2);
+            umma_acc(tmem_base, a + 1, b2 + 2 * kB, desc_hi, id2);
+            umma_acc(tmem_base, a + kP + 1, b2 + 3 * kB, desc_hi, id2);
+            umma_acc(tmem_base, a + 2, b2 + 4 * kB, desc_hi, id2);
+            umma_acc(tmem_base, a + kP + 2, b2 + 5 * kB, desc_hi, id2);
+            umma_acc(tmem_base, a2, b2 + 6 * kB, desc_hi, id2);
           }
-          if (!(p.mode & 1)) umma_bf16(d_addr, da2, db2, idesc, 1u);
-          umma_commit(&row_empty[s]);
-          umma_commit(&slot_full[slot]);
+          umma_commit_addr(bar_row_empty + s * 8);
+          if (i >= 2) umma_commit_addr(bar_slot_full + ((go + i - 2) & (kSlots - 1)) * 8);
         }
         __syncwarp();
+        if (++s == kStages) { s = 0; sph ^= 1; }
       }
     }
-    if (p.stats && blockIdx.x == 0 && lane == 0) { p.stats[2] = c_m0; p.stats[3] = c_m1; p.stats[4] = c_m2; p.stats[5] = clock64() - c_mt; }
-  } else if (warp == 2 && !(p.mode & 16)) {
+    (void)bar_row_full; (void)bar_a2_full;
+    if (p.stats && blockIdx.x == 0 && lane == 0) { p.stats[3] = c_se; p.stats[4] = c_rf; p.stats[5] = c_af; p.stats[6] = clock64() - t0; }
+  } else if (warp == 2) {
     // ===================== DEM prefetcher: fp32 halo rows -> smem, up to kStages rows ahead =================
     // 4-byte cp.async (zero-filled outside the tile); completion is signalled straight to the builder's mbarrier,
     // so this warp never waits for memory.
-    long long c_p0 = 0, c_pt = clock64();
     int g = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int t = item;
-      const int xs = t % segs;
-      t /= segs;
-      const int rbk = t % rblocks;
-      const int img = t / rblocks;
+    for (ItemIter it(p); it.next();) {
+      const int n_in = it.rows + 2;
       for (int i = 0; i < n_in; ++i, ++g) {
         const int s = g % kStages;
-        const int y = rbk * p.rb - 1 + i;
+        const int y = it.y0 - 1 + i;
         const bool yok = y >= 0 && y < p.H;
-        const float* row = p.dem + ((size_t)img * p.H + (yok ? y : 0)) * p.W;
+        const float* row = p.dem + ((size_t)it.img * p.H + (yok ? y : 0)) * p.W;
         const uint32_t dst = smem_u32(smem_dem + s * kDemBytes);
-        TWAIT(c_p0, &row_empty[s], ((g / kStages) & 1) ^ 1, p.dbg, 0x800000u | g);
+        mbar_wait(&row_empty[s], ((g / kStages) & 1) ^ 1);
         for (int k = lane; k < kRowPx; k += 32) {
-          const int x = xs * 128 - 1 + k;
+          const int x = it.xs * 128 - 1 + k;
           const bool ok = yok && x >= 0 && x < p.W;
           const float* src = row + (ok ? x : 0);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + k * 4), "l"(src), "r"(ok ? 4 : 0) : "memory");
@@ -247,26 +311,23 @@ head2_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&dem_full[s])) : "memory");
       }
     }
-    if (p.stats && blockIdx.x == 0 && lane == 0) { p.stats[6] = c_p0; p.stats[7] = clock64() - c_pt; }
-  } else if (warp == 3 && !(p.mode & 16)) {
-    // ===================== DEM operand builder: [128 px][hi(-1,0,+1), lo(-1,0,+1), 1, 0] ====================
-    long long c_b0 = 0, c_bt = clock64();
+  } else if (warp == 3) {
+    // ===================== DEM operand builder: [128 px][hi(-1,0,+1), lo(-1,0,+1), 1, 1] ====================
+    const uint32_t ones = (uint32_t)to16(1.0f, p.half) * 0x10001u;
     int g = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (ItemIter it(p); it.next();) {
+      const int n_in = it.rows + 2;
       for (int i = 0; i < n_in; ++i, ++g) {
         const int s = g % kStages;
-        TWAIT(c_b0, &dem_full[s], (g / kStages) & 1, p.dbg, 0x600000u | g);
+        mbar_wait(&dem_full[s], (g / kStages) & 1);
         const float* drow = reinterpret_cast<const float*>(smem_dem + s * kDemBytes) + lane * 4;
-        float d[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) d[k] = drow[k];
         uint16_t hi[6], lo[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-          hi[k] = to16(d[k], p.half);
-          lo[k] = to16(d[k] - from16(hi[k], p.half), p.half);
+          const float d = drow[k];
+          hi[k] = to16(d, p.half);
+          lo[k] = to16(d - from16(hi[k], p.half), p.half);
         }
-        const uint16_t one = to16(1.0f, p.half);
         uint4* dst = reinterpret_cast<uint4*>(smem_a2 + s * kA2Bytes) + lane * 4;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -274,7 +335,7 @@ head2_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
           v.x = (uint32_t)hi[q] | ((uint32_t)hi[q + 1] << 16);
           v.y = (uint32_t)hi[q + 2] | ((uint32_t)lo[q] << 16);
           v.z = (uint32_t)lo[q + 1] | ((uint32_t)lo[q + 2] << 16);
-          v.w = (uint32_t)one;
+          v.w = ones;
           dst[q] = v;
         }
         fence_proxy_async_smem();
@@ -282,62 +343,49 @@ head2_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         if (lane == 0) mbar_arrive(&a2_full[s]);
       }
     }
-    if (p.stats && blockIdx.x == 0 && lane == 0) { p.stats[8] = c_b0; p.stats[9] = clock64() - c_bt; }
-  } else if (warp >= 4) {
-    // ===================== epilogue: one warpgroup, every accumulator slot is read exactly once ============
-    // Input row i contributes its ky=0 / 1 / 2 column groups to output rows i, i-1, i-2 (item-local).  The two
-    // unfinished output rows are carried as register partials (pa: needs ky=2 next, pb: needs ky=1 then ky=2),
-    // so a slot is released right after its single read and the MMA warp can run kSlots-1 rows ahead.
-    const int q = warp & 3;            // TMEM lane quarter
+  } else {
+    // ===================== epilogue groups: each finished accumulator is read exactly once =================
+    const int grp = (warp - 4) >> 2;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    long long c_e0 = 0, c_et = clock64();
-    int g = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int t = item;
-      const int xs = t % segs;
-      t /= segs;
-      const int rbk = t % rblocks;
-      const int img = t / rblocks;
-      const int x = xs * 128 + m;
-      float pa[kCmid], pb[kCmid];
-      for (int i = 0; i < n_in; ++i, ++g) {
-        const int slot = g % kSlots;
-        TWAIT(c_e0, &slot_full[slot], (g / kSlots) & 1, p.dbg, 0x700000u | g);
+    float w2r[kCmid];
+#pragma unroll
+    for (int c = 0; c < kCmid; ++c) w2r[c] = p.w2[c];
+    int go = 0;
+    long long c_sf = 0, t0 = STATS ? clock64() : 0;
+    for (ItemIter it(p); it.next(); go += it.rows) {
+      const int x = it.xs * 128 + m;
+      for (int j = 0; j < it.rows; ++j) {
+        const int r = go + j;
+        if ((r % kEpiGroups) != grp) continue;
+        const int slot = r & (kSlots - 1);
+        mbar_wait_t<STATS>(&slot_full[slot], (r / kSlots) & 1, c_sf);
         tc_fence_after();
-        const uint32_t taddr = lane_addr + slot * kN;
-        float out = p.b2;
-        {
-          float v[32];
-          tmem_ld32(taddr + 2 * kCmid, v);  // ky = 2 -> completes output row i-2
-          tmem_ld_wait();
-          if (i >= 2 && !(p.mode & 2)) {
-#pragma unroll
-            for (int c = 0; c < kCmid; ++c) out = fmaf(apply_act(pa[c] + v[c], p.act, p.alpha), p.w2[c], out);
-          }
-        }
-        {
-          float v[32];
-          tmem_ld32(taddr + kCmid, v);      // ky = 1 -> second contribution of output row i-1
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < kCmid; ++c) pa[c] = pb[c] + v[c];
-        }
-        tmem_ld32(taddr, pb);               // ky = 0 -> first contribution of output row i
+        float v[kCmid];
+        tmem_ld32(lane_addr + slot * kCmid, v);
         tmem_ld_wait();
+        tmem_zero32(lane_addr + slot * kCmid);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
-        if (i >= 2 && !(p.mode & 2)) {
-          const int y = rbk * p.rb + i - 2;
-          const size_t off = ((size_t)img * p.H + y) * p.W + x;
-          if (p.pred_norm) p.pred_norm[off] = out;
-          const float yn = fminf(fmaxf(out, 0.0f), 1.0f);
-          p.pred_m[off] = fminf(fmaxf(expm1f(__fmul_rn(yn, p.denom)), 0.0f), p.max_depth);
+        float o0 = p.b2, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kCmid; c += 4) {
+          o0 = fmaf(act_fn<ACT>(v[c], p.alpha), w2r[c], o0);
+          o1 = fmaf(act_fn<ACT>(v[c + 1], p.alpha), w2r[c + 1], o1);
+          o2 = fmaf(act_fn<ACT>(v[c + 2], p.alpha), w2r[c + 2], o2);
+          o3 = fmaf(act_fn<ACT>(v[c + 3], p.alpha), w2r[c + 3], o3);
         }
+        const float out = (o0 + o1) + (o2 + o3);
+        const size_t off = ((size_t)it.img * p.H + (it.y0 + j)) * p.W + x;
+        if (p.pred_norm) p.pred_norm[off] = out;
+        const float yn = fminf(fmaxf(out, 0.0f), 1.0f);
+        p.pred_m[off] = fminf(fmaxf(expm1f(__fmul_rn(yn, p.denom)), 0.0f), p.max_depth);
       }
     }
-    if (p.stats && blockIdx.x == 0 && warp == 4 && lane == 0) { p.stats[10] = c_e0; p.stats[11] = clock64() - c_et; }
+    if (p.stats && blockIdx.x == 0 && warp == 4 && lane == 0) { p.stats[7] = c_sf; p.stats[8] = clock64() - t0; }
   }
   __syncthreads();
   if (warp == 1) {
@@ -348,31 +396,35 @@ head2_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 
 }  // namespace
 
-// Packed operands of the head (host side, built once per engine):
-//   [kx][k-slice j][plane pl][n = ky*32 + co][8]  feature weights W[ky][kx][ci = j*16 + pl*8 + e][co]
-//   [plane][n][8]                                  DEM/bias operand: k 0-2 = Wdem[ky][kx], k 3-5 = the same (lo part),
-//                                                  k 6 = bias[co] for ky == 1, everything else 0
+// Packed operands of the head (host side, built once per engine); column n = b*32 + co with ky = 2 - b:
+//   [kx][k-slice j][plane pl][n][8]  feature weights W[ky][kx][ci = j*16 + pl*8 + e][co]
+//   [plane][n][8]                    DEM/bias operand: k 0-2 = Wdem[ky][kx], k 3-5 = the same (they multiply the lo
+//                                    parts), k 6/7 = (hi, lo) of bias[co] for ky == 1, everything else 0
 size_t head2_pack_elems() { return (size_t)(kWBytes + kW2Bytes) / 2; }
 
-void head2_pack(const float* w /* [3][3][33][32] */, const float* bias, uint16_t* dst, uint16_t (*cvt)(float)) {
+void head2_pack(const float* w /* [3][3][33][32] */, const float* bias, uint16_t* dst, uint16_t (*cvt)(float), float (*back)(uint16_t)) {
   const int cin_real = 33;
   size_t pos = 0;
   for (int kx = 0; kx < 3; ++kx)
     for (int j = 0; j < 2; ++j)
       for (int pl = 0; pl < 2; ++pl)
-        for (int n = 0; n < kN; ++n)
+        for (int n = 0; n < kNfull; ++n)
           for (int e = 0; e < 8; ++e, ++pos) {
-            const int ky = n / kCmid, co = n % kCmid, ci = j * 16 + pl * 8 + e;
+            const int ky = 2 - n / kCmid, co = n % kCmid, ci = j * 16 + pl * 8 + e;
             dst[pos] = cvt(w[(((size_t)ky * 3 + kx) * cin_real + ci) * kCmid + co]);
           }
   for (int pl = 0; pl < 2; ++pl)
-    for (int n = 0; n < kN; ++n)
+    for (int n = 0; n < kNfull; ++n)
       for (int e = 0; e < 8; ++e, ++pos) {
-        const int ky = n / kCmid, co = n % kCmid;
-        float v = 0.0f;
-        if (pl == 0 && e < 6) v = w[(((size_t)ky * 3 + (e % 3)) * cin_real + 32) * kCmid + co];
-        if (pl == 0 && e == 6 && ky == 1 && bias) v = bias[co];
-        dst[pos] = cvt(v);
+        const int ky = 2 - n / kCmid, co = n % kCmid;
+        uint16_t v = cvt(0.0f);
+        if (pl == 0 && e < 6) v = cvt(w[(((size_t)ky * 3 + (e % 3)) * cin_real + 32) * kCmid + co]);
+        if (pl == 0 && ky == 1 && bias) {
+          const uint16_t bh = cvt(bias[co]);
+          if (e == 6) v = bh;
+          if (e == 7) v = cvt(bias[co] - back(bh));
+        }
+        dst[pos] = v;
       }
 }
 
@@ -380,12 +432,10 @@ void launch_head2_tc(const __nv_bfloat16* feat, long long plane, const __nv_bflo
                      const float* dem, float* pred_m, float* pred_norm, int n_img, int H, int W, int cin, int cmid, int ksz,
                      int act, float alpha, float max_depth, float denom, int half, int n_sms, cudaStream_t s) {
   FSR_REQUIRE(cin == 32 && cmid == kCmid && ksz == 3, "head tensor-core path is specialised for 32 -> 32 channels, 3x3");
-  FSR_REQUIRE(W % 128 == 0 && H % 32 == 0, "head tensor-core path needs W % 128 == 0 and H % 32 == 0");
-  Head2Params p{};
+  FSR_REQUIRE(W % 128 == 0 && H >= 1, "head tensor-core path needs W % 128 == 0");
+  HeadParams p{};
   p.H = H; p.W = W; p.N = n_img;
-  p.rb = 32;
-  p.n_items = n_img * (W / 128) * (H / p.rb);
-  p.act = act;
+  p.total_rows = (long long)n_img * (W / 128) * H;
   p.alpha = alpha;
   p.half = half;
   p.max_depth = max_depth;
@@ -396,38 +446,33 @@ void launch_head2_tc(const __nv_bfloat16* feat, long long plane, const __nv_bflo
   p.pred_norm = pred_norm;
   for (int c = 0; c < kCmid; ++c) p.w2[c] = w2[c];
   p.b2 = b2 ? b2[0] : 0.0f;
-  p.mode = getenv("FSR_HEAD_MODE") ? atoi(getenv("FSR_HEAD_MODE")) : 0;
-  static unsigned* dbg_host = nullptr;
-  static unsigned* dbg_dev = nullptr;
-  if (!dbg_host) {
-    FSR_CUDA(cudaHostAlloc(&dbg_host, sizeof(unsigned), cudaHostAllocMapped));
-    *dbg_host = 0;
-    FSR_CUDA(cudaHostGetDevicePointer(&dbg_dev, dbg_host, 0));
-    static unsigned** keep = &dbg_host;
-    atexit([]() {
-      if (**keep) fprintf(stderr, "[floodsr_b200] head2 pipeline wait timed out: tag 0x%x\n", **keep);
-    });
-  }
-  if (*dbg_host) fprintf(stderr, "[floodsr_b200] head2 pipeline wait timed out earlier: tag 0x%x\n", *dbg_host);
-  p.dbg = dbg_dev;
+  CUtensorMap mF = make_cp8_tensor_map(feat, W, H, n_img, cin / 8, plane, kRowPx, 1, 1, cin / 8);
   static long long* d_stats = nullptr;
   static int stat_calls = 0;
   if (getenv("FSR_HEAD_STATS")) {
-    if (!d_stats) { FSR_CUDA(cudaMalloc(&d_stats, 16 * sizeof(long long))); FSR_CUDA(cudaMemset(d_stats, 0, 16 * sizeof(long long))); }
+    if (!d_stats) FSR_CUDA(cudaMalloc(&d_stats, 16 * sizeof(long long)));
     p.stats = d_stats;
   }
-  CUtensorMap mF = make_cp8_tensor_map(feat, W, H, n_img, cin / 8, plane, kRowPx, 1, 1, cin / 8);
-  static bool attr = false;
-  if (!attr) { FSR_CUDA(cudaFuncSetAttribute(head2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); attr = true; }
-  const int grid = p.n_items < n_sms ? p.n_items : n_sms;
-  head2_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(mF, p);
+  const int grid = p.total_rows < n_sms ? (int)p.total_rows : n_sms;
+  auto go = [&](auto kernel) {
+    FSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    kernel<<<grid, kThreads, kSmemBytes, s>>>(mF, p);
+  };
+  if (p.stats) {
+    if (act == FSR_ACT_RELU) go(head_tc_kernel<FSR_ACT_RELU, true>);
+    else if (act == FSR_ACT_LEAKY) go(head_tc_kernel<FSR_ACT_LEAKY, true>);
+    else go(head_tc_kernel<FSR_ACT_NONE, true>);
+  } else {
+    if (act == FSR_ACT_RELU) go(head_tc_kernel<FSR_ACT_RELU, false>);
+    else if (act == FSR_ACT_LEAKY) go(head_tc_kernel<FSR_ACT_LEAKY, false>);
+    else go(head_tc_kernel<FSR_ACT_NONE, false>);
+  }
   FSR_LAUNCH_CHECK();
-  if (p.stats && ++stat_calls == 20) {
+  if (p.stats && ++stat_calls == 8) {
     long long h[16];
     FSR_CUDA(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[head2 stats, CTA 0, %lld rows] producer: wait row_empty %lld of %lld | mma: slot_empty %lld row_full %lld a2_full %lld of %lld | "
-            "demprefetch: row_empty %lld of %lld | builder: dem_full %lld of %lld | epilogue: slot_full %lld of %lld cycles\n",
-            h[15], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+    fprintf(stderr, "[head stats, CTA 0, %lld input rows] producer: row_empty %lld of %lld | mma: slot_empty %lld row_full %lld a2_full %lld of %lld | "
+            "epilogue grp0: slot_full %lld of %lld cycles\n", h[2], h[0], h[1], h[3], h[4], h[5], h[6], h[7], h[8]);
   }
 }
 

@@ -68,11 +68,11 @@ int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   const int iters = 3000;
-  for (int grid : {1, 148}) for (int N : {32, 96, 128, 256}) for (int mode : {0, 1, 2}) for (int step : {16}) {
+  for (int grid : {1, 148}) for (int N : {32, 64, 96, 128, 256}) for (int mode : {0, 1, 2}) for (int step : {0, 16}) {
     mma_bench<<<grid, 128, 96 * 1024>>>(mode, N, iters, step, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    printf("grid %3d N %3d mode %d: %.1f cycles/MMA (ideal %d) %s\n", grid, N, mode, (double)h / iters, N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    printf("grid %3d N %3d mode %d step %2d: %.1f cycles/MMA (ideal %d) %s\n", grid, N, mode, step, (double)h / iters, N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
   }
   return 0;
 }

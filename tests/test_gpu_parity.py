@@ -329,3 +329,72 @@ def test_band_sharding_is_bit_identical_to_single_pass(engine, h, w, world):
         got[plan.row0 : plan.row0 + plan.n_rows] = rows.cpu().numpy()
         halo = halo_out
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core modes (tcgen05, bf16 / fp16 operands, fp32 accumulate): north-star tolerance 1e-2 m and the same
+# wet/dry mask at a 0.01 m threshold
+# ---------------------------------------------------------------------------------------------------------
+
+# fp16 operands meet the north-star bound (1e-2 m); bf16 operands (3 fewer mantissa bits) are measured at ~2.5e-2 m on
+# the random-init H1 graph, i.e. they do NOT meet it here: the bound below only guards against regressions and
+# DESIGN.md states the measured figure.
+TC_TOL_M = {"fp16": 1e-2, "bf16": 5e-2}
+TC_TOL_NORM = {"fp16": 2e-3, "bf16": 1e-2}
+WET_M = 0.01
+
+
+@pytest.fixture(scope="module", params=["bf16", "fp16"])
+def tc_engine(request, h1_model_fp):
+    from floodsr_b200.engine import EngineB200
+
+    eng = EngineB200(h1_model_fp, precision=request.param)
+    yield eng
+    eng.close()
+
+
+def _assert_tc_close(eng, got_m, want_m):
+    tol = TC_TOL_M[eng.precision]
+    err = np.abs(got_m - want_m)
+    assert float(err.max()) <= tol, float(err.max())
+    flips = (got_m > WET_M) != (want_m > WET_M)
+    # a pixel may only change class when the oracle itself sits on the threshold (closer than the actual error there)
+    assert not flips.any() or float(np.abs(want_m[flips] - WET_M).max()) <= float(err[flips].max()) <= tol
+    assert flips.mean() <= 2e-3, flips.mean()
+
+
+@pytest.mark.parametrize("case", mg.tile_cases(), ids=lambda c: c[0])
+def test_tc_run_tile_matches_oracle(tc_engine, oracle_engine, case):
+    name, depth, dem, kw = case
+    want = oracle_engine.run_tile(depth, dem, **kw)
+    got = tc_engine.run_tile(depth, dem, **kw)
+    assert got["dem_stats_used"] == want["dem_stats_used"]  # normalisation statistics stay bit-exact in every mode
+    _assert_tc_close(tc_engine, got["prediction_m"], want["prediction_m"])
+    assert np.abs(got["prediction_norm"] - want["prediction_norm"]).max() <= TC_TOL_NORM[tc_engine.precision]
+
+
+@pytest.mark.parametrize("b", [1, 3, 7])
+def test_tc_batches_split_rows_evenly_and_match_fp32_engine(tc_engine, engine, b):
+    """Any batch size: the head kernel splits the batch's strip rows into equal ranges per SM (ragged items)."""
+    depth = np.stack([synth_depth(32, 32, seed=60 + i) for i in range(b)])
+    dem = np.stack([synth_dem(512, 512, seed=60 + i) for i in range(b)])
+    want = engine.run_tiles(depth, dem)
+    got = tc_engine.run_tiles(depth, dem)
+    again = tc_engine.run_tiles(depth, dem)
+    assert np.array_equal(got["prediction_m"], again["prediction_m"])  # deterministic
+    assert got["dem_stats_used"] == want["dem_stats_used"]
+    for i in range(b):
+        _assert_tc_close(tc_engine, got["prediction_m"][i], want["prediction_m"][i])
+        one = tc_engine.run_tile(depth[i], dem[i])
+        assert np.array_equal(one["prediction_m"], got["prediction_m"][i])  # independent of the batch it ran in
+
+
+def test_tc_run_raster_matches_oracle_tile_loop(tc_engine, oracle_engine):
+    from oracle.stitch_np import run_tiled
+
+    h, w = 976, 1104
+    depth, dem = synth_raster(h, w, seed=h + w)
+    want, n_tiles, summary = run_tiled(oracle_engine, depth, dem, window_method="feather", overlap_lr=8)
+    got, got_n, got_summary = tc_engine.run_raster(depth, dem)
+    assert got_n == n_tiles and got_summary == summary
+    _assert_tc_close(tc_engine, got, want)
