@@ -39,7 +39,7 @@ namespace {
 constexpr int kCmid = 32;
 constexpr int kNfull = 3 * kCmid;                 // widest MMA: three adjacent output-row accumulators
 constexpr int kSlots = 16;                        // 16 x 32 fp32 columns = the whole TMEM
-constexpr int kStages = 8;
+constexpr int kStages = 18;                       // input rows in flight per SM: ~150 KB, sized for HBM latency
 constexpr int kRowPx = 130;                       // 128 + left/right halo pixel
 constexpr int kPlaneBytes = kRowPx * 16;          // 2080
 constexpr int kRowBytes = 4 * kPlaneBytes;        // 32 feature channels = 4 planes
@@ -50,7 +50,7 @@ constexpr int kA2Bytes = 128 * 16;                // DEM operand plane per stage
 constexpr int kDemBytes = 640;                    // per-stage fp32 DEM halo row (128-byte aligned)
 constexpr int kEpiGroups = 2;
 constexpr int kThreads = 128 + 128 * kEpiGroups;
-constexpr int kSmemBytes = 160 * 1024;            // > half an SM's shared memory: exactly one CTA per SM (TMEM is exclusive)
+constexpr int kSmemBytes = kWBytes + kW2Bytes + kStages * (kRowBytes + kA2Bytes + kDemBytes) + kA2Bytes + 1024;  // one CTA per SM
 
 struct HeadParams {
   int H, W, N;          // HR tile extent and tiles in this launch
@@ -68,6 +68,26 @@ struct HeadParams {
 };
 
 // mbarrier wait that adds the cycles spent to `cnt` (pipeline diagnostics; `cnt` is dead code when unused)
+// mbarrier wait for roles that normally wait long (epilogue, producers): try_wait with a suspend-time hint, so the
+// polling does not compete with the tensor core for shared-memory bandwidth.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
 template <bool STATS>
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& cnt) {
   if (STATS) {
@@ -152,14 +172,12 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
   uint8_t* smem_w2 = smem_w + kWBytes;                          // 3072 B
   uint8_t* smem_rows = smem_w2 + kW2Bytes;                      // kStages x 8320 B (128-B aligned)
   uint8_t* smem_a2 = smem_rows + kStages * kRowBytes;           // kStages x 2048 B
-  uint8_t* smem_zero = smem_a2 + kStages * kA2Bytes;            // kStages x 2048 B of zeros: upper K plane of the DEM operand,
-                                                                // one per stage so the plane stride (LBO) is a constant
-  uint8_t* smem_dem = smem_zero + kStages * kA2Bytes;           // kStages x 640 B fp32 DEM halo rows
+  uint8_t* smem_zero = smem_a2 + kStages * kA2Bytes;            // 2048 B of zeros: upper K plane of every DEM operand
+  uint8_t* smem_dem = smem_zero + kA2Bytes;                     // kStages x 640 B fp32 DEM halo rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dem + kStages * kDemBytes);
   uint64_t* w_full = bars;
-  uint64_t* row_full = bars + 1;                 // [kStages]  TMA -> MMA
-  uint64_t* a2_full = row_full + kStages;        // [kStages]  DEM builder -> MMA
-  uint64_t* row_empty = a2_full + kStages;       // [kStages]  MMA -> producers
+  uint64_t* row_full = bars + 1;                 // [kStages]  TMA bytes + DEM builder arrival -> MMA
+  uint64_t* row_empty = row_full + kStages;      // [kStages]  MMA -> producers
   uint64_t* dem_full = row_empty + kStages;      // [kStages]  DEM prefetcher (32 cp.async arrivals) -> builder
   uint64_t* slot_full = dem_full + kStages;      // [kSlots]   MMA -> epilogue
   uint64_t* slot_empty = slot_full + kSlots;     // [kSlots]   epilogue (4 warps) -> MMA
@@ -172,8 +190,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     if (lane == 0) {
       mbar_init(w_full, 1);
       for (int i = 0; i < kStages; ++i) {
-        mbar_init(&row_full[i], 1);
-        mbar_init(&a2_full[i], 1);
+        mbar_init(&row_full[i], 2);
         mbar_init(&row_empty[i], 1);
         mbar_init(&dem_full[i], 32);
       }
@@ -188,7 +205,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     tmem_relinquish();
   }
   if (warp == 2) {
-    for (int i = lane; i < kStages * kA2Bytes / 16; i += 32) reinterpret_cast<uint4*>(smem_zero)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < kA2Bytes / 16; i += 32) reinterpret_cast<uint4*>(smem_zero)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -209,18 +226,18 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     if (lane == 0) {
       mbar_expect_tx(w_full, kWBytes + kW2Bytes);
       bulk_load_1d(smem_w, p.wpack, kWBytes + kW2Bytes, w_full);
-      int g = 0;  // running input-row counter of this CTA
-      long long c0 = 0, t0 = STATS ? clock64() : 0;
+      int g = 0, s = 0;  // running input-row counter of this CTA and its smem stage
+      uint32_t ph = 1;
       for (ItemIter it(p); it.next();) {
         const int n_in = it.rows + 2;
         for (int i = 0; i < n_in; ++i, ++g) {
-          const int s = g % kStages;
-          mbar_wait_t<STATS>(&row_empty[s], ((g / kStages) & 1) ^ 1, c0);
+          mbar_wait_relaxed(&row_empty[s], ph);
           mbar_expect_tx(&row_full[s], kRowBytes);
           tma_load_5d(smem_rows + s * kRowBytes, &tmF, &row_full[s], 0, it.xs * 128 - 1, it.y0 - 1 + i, it.img, 0);
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
-      if (STATS && p.stats && blockIdx.x == 0) { p.stats[0] = c0; p.stats[1] = clock64() - t0; p.stats[2] = g; }
+      if (STATS && p.stats && blockIdx.x == 0) p.stats[2] = g;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================================================================
@@ -228,80 +245,101 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     // is light: the loop is warp-uniform, descriptors are 32-bit bases plus immediates, ring indices and barrier
     // phases are carried incrementally, and only the tcgen05 instructions themselves are issued by one lane.
     const uint32_t idesc0 = idesc_16(128, 0, p.half);  // + (N >> 3) << 17 with N = 32 * accumulators
+    const uint32_t idesc96 = idesc0 + (3u << 19);
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
     mbar_wait(w_full, 0);
     const uint32_t b_lo0 = desc_lo(smem_u32(smem_w), kNfull * 16);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem_rows), kPlaneBytes);
-    const uint32_t a2_lo0 = desc_lo(smem_u32(smem_a2), kStages * kA2Bytes);
-    const uint32_t bar_row_full = smem_u32(row_full), bar_a2_full = smem_u32(a2_full), bar_row_empty = smem_u32(row_empty);
-    const uint32_t bar_slot_full = smem_u32(slot_full);
+    // DEM operand of stage s: plane 0 at a2 + s * 2 KB, plane 1 = the shared zero plane, i.e. LBO shrinks as s grows:
+    // lo(s) = lo(0) + s * (128 - (128 << 16))
+    const uint32_t a2_lo0 = desc_lo(smem_u32(smem_a2), smem_u32(smem_zero) - smem_u32(smem_a2));
+    constexpr uint32_t kA2Step = (kA2Bytes >> 4) - ((kA2Bytes >> 4) << 16);
+    const uint32_t bar_full0 = smem_u32(row_full), bar_empty0 = smem_u32(row_empty);
+    const uint32_t bar_slot_full = smem_u32(slot_full), bar_slot_empty = smem_u32(slot_empty);
     const bool leader = elect_one();
-    int s = 0;            // smem stage of the current input row
-    uint32_t sph = 0;     // its barrier phase
+    constexpr uint32_t kB = kWStep >> 4, kP = (2 * kPlaneBytes) >> 4;
+    // per-stage values, carried incrementally
+    int s = 0;
+    uint32_t sph = 0, a = a_lo0, a2 = a2_lo0, bar_full = bar_full0, bar_empty = bar_empty0;
     int go = 0;           // output rows of earlier items
-    long long c_se = 0, c_rf = 0, c_af = 0, t0 = STATS ? clock64() : 0;
+    long long c_se = 0, c_rf = 0, t0 = STATS ? clock64() : 0;
     for (ItemIter it(p); it.next(); go += it.rows) {
       const int n_in = it.rows + 2;
       for (int i = 0; i < n_in; ++i) {
-        if (i < it.rows)  // output row i gets its first contribution (ky = 0) from this input row: its slot must be free
-          mbar_wait_t<STATS>(&slot_empty[(go + i) & (kSlots - 1)], (((go + i) / kSlots) & 1) ^ 1, c_se);
+        const int R = go + i;  // ring index of the output row this input row opens (ky = 0)
+        if (i < it.rows)       // its slot must have been read (and re-zeroed) by the epilogue
+          mbar_wait_t<STATS>(&slot_empty[R & (kSlots - 1)], ((R / kSlots) & 1) ^ 1, c_se);
         mbar_wait_t<STATS>(&row_full[s], sph, c_rf);
-        mbar_wait_t<STATS>(&a2_full[s], sph, c_af);
         tc_fence_after();
-        // output rows [jlo, jhi] accumulate from this input row; their slots are adjacent unless the ring wraps
-        const int jlo = i - 2 > 0 ? i - 2 : 0;
-        const int jhi = i < it.rows - 1 ? i : it.rows - 1;
-        const int n = jhi - jlo + 1;
-        const int sa = (go + jlo) & (kSlots - 1);
-        const int n1 = n < kSlots - sa ? n : kSlots - sa;
-        const uint32_t d1 = tmem_base + sa * kCmid;
-        const uint32_t id1 = idesc0 + ((uint32_t)n1 << 19);
-        const uint32_t b1 = b_lo0 + (uint32_t)(jlo - (i - 2)) * kCmid;  // weight rows (16 B each) of ky = i - jlo first
-        const uint32_t a = a_lo0 + s * (kRowBytes >> 4);
-        const uint32_t a2 = a2_lo0 + s * (kA2Bytes >> 4);
-        constexpr uint32_t kB = kWStep >> 4, kP = (2 * kPlaneBytes) >> 4;
-        if (leader) {
-          umma_acc(d1, a, b1, desc_hi, id1);
-          umma_acc(d1, a + kP, b1 + kB, desc_hi, id1);
-          umma_acc(d1, a + 1, b1 + 2 * kB, desc_hi, id1);
-          umma_acc(d1, a + kP + 1, b1 + 3 * kB, desc_hi, id1);
-          umma_acc(d1, a + 2, b1 + 4 * kB, desc_hi, id1);
-          umma_acc(d1, a + kP + 2, b1 + 5 * kB, desc_hi, id1);
-          umma_acc(d1, a2, b1 + 6 * kB, desc_hi, id1);
-          if (n1 < n) {
-            const uint32_t id2 = idesc0 + ((uint32_t)(n - n1) << 19);
-            const uint32_t b2 = b1 + n1 * kCmid;
-            umma_acc(tmem_base, a, b2, desc_hi, id2);
-            umma_acc(tmem_base, a + kP, b2 + kB, desc_hi, id2);
-            umma_acc(tmem_base, a + 1, b2 + 2 * kB, desc_hi, id2);
-            umma_acc(tmem_base, a + kP + 1, b2 + 3 * kB, desc_hi, id2);
-            umma_acc(tmem_base, a + 2, b2 + 4 * kB, desc_hi, id2);
-            umma_acc(tmem_base, a + kP + 2, b2 + 5 * kB, desc_hi, id2);
-            umma_acc(tmem_base, a2, b2 + 6 * kB, desc_hi, id2);
+        const int sa = (R - 2) & (kSlots - 1);
+        if (i >= 2 && i < it.rows && sa <= kSlots - 3) {
+          // steady state: three adjacent accumulators, one N = 96 MMA per K step
+          const uint32_t d = tmem_base + sa * kCmid;
+          if (leader) {
+            umma_acc(d, a, b_lo0, desc_hi, idesc96);
+            umma_acc(d, a + kP, b_lo0 + kB, desc_hi, idesc96);
+            umma_acc(d, a + 1, b_lo0 + 2 * kB, desc_hi, idesc96);
+            umma_acc(d, a + kP + 1, b_lo0 + 3 * kB, desc_hi, idesc96);
+            umma_acc(d, a + 2, b_lo0 + 4 * kB, desc_hi, idesc96);
+            umma_acc(d, a + kP + 2, b_lo0 + 5 * kB, desc_hi, idesc96);
+            umma_acc(d, a2, b_lo0 + 6 * kB, desc_hi, idesc96);
+            umma_commit_addr(bar_empty);
+            umma_commit_addr(bar_slot_full + sa * 8);
           }
-          umma_commit_addr(bar_row_empty + s * 8);
-          if (i >= 2) umma_commit_addr(bar_slot_full + ((go + i - 2) & (kSlots - 1)) * 8);
+        } else {
+          // item borders (fewer than three target rows) and ring wrap-around (two MMAs per K step)
+          const int jlo = i - 2 > 0 ? i - 2 : 0;
+          const int jhi = i < it.rows - 1 ? i : it.rows - 1;
+          const int n = jhi - jlo + 1;
+          const int s1 = (go + jlo) & (kSlots - 1);
+          const int n1 = n < kSlots - s1 ? n : kSlots - s1;
+          const uint32_t d1 = tmem_base + s1 * kCmid;
+          const uint32_t id1 = idesc0 + ((uint32_t)n1 << 19);
+          const uint32_t b1 = b_lo0 + (uint32_t)(jlo - (i - 2)) * kCmid;  // weight rows (16 B each) of ky = i - jlo first
+          if (leader) {
+            umma_acc(d1, a, b1, desc_hi, id1);
+            umma_acc(d1, a + kP, b1 + kB, desc_hi, id1);
+            umma_acc(d1, a + 1, b1 + 2 * kB, desc_hi, id1);
+            umma_acc(d1, a + kP + 1, b1 + 3 * kB, desc_hi, id1);
+            umma_acc(d1, a + 2, b1 + 4 * kB, desc_hi, id1);
+            umma_acc(d1, a + kP + 2, b1 + 5 * kB, desc_hi, id1);
+            umma_acc(d1, a2, b1 + 6 * kB, desc_hi, id1);
+            if (n1 < n) {
+              const uint32_t id2 = idesc0 + ((uint32_t)(n - n1) << 19);
+              const uint32_t b2 = b1 + n1 * kCmid;
+              umma_acc(tmem_base, a, b2, desc_hi, id2);
+              umma_acc(tmem_base, a + kP, b2 + kB, desc_hi, id2);
+              umma_acc(tmem_base, a + 1, b2 + 2 * kB, desc_hi, id2);
+              umma_acc(tmem_base, a + kP + 1, b2 + 3 * kB, desc_hi, id2);
+              umma_acc(tmem_base, a + 2, b2 + 4 * kB, desc_hi, id2);
+              umma_acc(tmem_base, a + kP + 2, b2 + 5 * kB, desc_hi, id2);
+              umma_acc(tmem_base, a2, b2 + 6 * kB, desc_hi, id2);
+            }
+            umma_commit_addr(bar_empty);
+            if (i >= 2) umma_commit_addr(bar_slot_full + sa * 8);
+          }
         }
         __syncwarp();
-        if (++s == kStages) { s = 0; sph ^= 1; }
+        a += kRowBytes >> 4; a2 += kA2Step; bar_full += 8; bar_empty += 8;
+        if (++s == kStages) { s = 0; sph ^= 1; a = a_lo0; a2 = a2_lo0; bar_full = bar_full0; bar_empty = bar_empty0; }
       }
     }
-    (void)bar_row_full; (void)bar_a2_full;
-    if (p.stats && blockIdx.x == 0 && lane == 0) { p.stats[3] = c_se; p.stats[4] = c_rf; p.stats[5] = c_af; p.stats[6] = clock64() - t0; }
+    (void)bar_full; (void)bar_slot_empty;
+    if (STATS && p.stats && blockIdx.x == 0 && lane == 0) { p.stats[3] = c_se; p.stats[4] = c_rf; p.stats[5] = 0; p.stats[6] = clock64() - t0; }
   } else if (warp == 2) {
     // ===================== DEM prefetcher: fp32 halo rows -> smem, up to kStages rows ahead =================
     // 4-byte cp.async (zero-filled outside the tile); completion is signalled straight to the builder's mbarrier,
     // so this warp never waits for memory.
-    int g = 0;
+    int s = 0;
+    uint32_t ph = 1;
     for (ItemIter it(p); it.next();) {
       const int n_in = it.rows + 2;
-      for (int i = 0; i < n_in; ++i, ++g) {
-        const int s = g % kStages;
+      for (int i = 0; i < n_in; ++i) {
         const int y = it.y0 - 1 + i;
         const bool yok = y >= 0 && y < p.H;
         const float* row = p.dem + ((size_t)it.img * p.H + (yok ? y : 0)) * p.W;
         const uint32_t dst = smem_u32(smem_dem + s * kDemBytes);
-        mbar_wait(&row_empty[s], ((g / kStages) & 1) ^ 1);
+        mbar_wait_relaxed(&row_empty[s], ph);
         for (int k = lane; k < kRowPx; k += 32) {
           const int x = it.xs * 128 - 1 + k;
           const bool ok = yok && x >= 0 && x < p.W;
@@ -309,17 +347,18 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + k * 4), "l"(src), "r"(ok ? 4 : 0) : "memory");
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&dem_full[s])) : "memory");
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 3) {
     // ===================== DEM operand builder: [128 px][hi(-1,0,+1), lo(-1,0,+1), 1, 1] ====================
     const uint32_t ones = (uint32_t)to16(1.0f, p.half) * 0x10001u;
-    int g = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (ItemIter it(p); it.next();) {
       const int n_in = it.rows + 2;
-      for (int i = 0; i < n_in; ++i, ++g) {
-        const int s = g % kStages;
-        mbar_wait(&dem_full[s], (g / kStages) & 1);
+      for (int i = 0; i < n_in; ++i) {
+        mbar_wait_relaxed(&dem_full[s], ph);
         const float* drow = reinterpret_cast<const float*>(smem_dem + s * kDemBytes) + lane * 4;
         uint16_t hi[6], lo[6];
 #pragma unroll
@@ -340,7 +379,8 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a2_full[s]);
+        if (lane == 0) mbar_arrive(&row_full[s]);
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -360,7 +400,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
         const int r = go + j;
         if ((r % kEpiGroups) != grp) continue;
         const int slot = r & (kSlots - 1);
-        mbar_wait_t<STATS>(&slot_full[slot], (r / kSlots) & 1, c_sf);
+        if (STATS) mbar_wait_t<STATS>(&slot_full[slot], (r / kSlots) & 1, c_sf); else mbar_wait_relaxed(&slot_full[slot], (r / kSlots) & 1);
         tc_fence_after();
         float v[kCmid];
         tmem_ld32(lane_addr + slot * kCmid, v);
@@ -471,8 +511,8 @@ void launch_head2_tc(const __nv_bfloat16* feat, long long plane, const __nv_bflo
   if (p.stats && ++stat_calls == 8) {
     long long h[16];
     FSR_CUDA(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[head stats, CTA 0, %lld input rows] producer: row_empty %lld of %lld | mma: slot_empty %lld row_full %lld a2_full %lld of %lld | "
-            "epilogue grp0: slot_full %lld of %lld cycles\n", h[2], h[0], h[1], h[3], h[4], h[5], h[6], h[7], h[8]);
+    fprintf(stderr, "[head stats, CTA 0, %lld input rows] mma: slot_empty %lld row_full %lld of %lld | epilogue grp0: slot_full %lld of %lld cycles\n",
+            h[2], h[3], h[4], h[6], h[7], h[8]);
   }
 }
 
