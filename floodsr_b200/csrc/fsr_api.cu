@@ -34,6 +34,7 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_REQUIRE(hdr_.hr_tile % 64 == 0, "hr tile must be a multiple of 64");
   FSR_REQUIRE(hdr_.out_tensor >= 2 && hdr_.out_tensor < hdr_.n_tensors, "bad output tensor");
   FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_BF16 || precision == FSR_PREC_FP16, "unknown precision mode");
+  if (const char* e = getenv("FSR_BAND_TILES")) band_tiles_ = std::max(1, atoi(e));
 
   const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
   big_.assign(tensors_.size(), 0);
@@ -80,9 +81,10 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
     FSR_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major != 10) throw Error(FSR_E_UNSUPPORTED, "the tensor-core backends need an sm_100 (Blackwell) device: tcgen05/TMEM/TMA");
     n_sms_ = prop.multiProcessorCount;
-    chunk_tiles_ = 256;
+    chunk_tiles_ = 1024;  // the batched low-resolution layers need many tiles per launch to fill 148 SMs
     hr_sub_ = 32;  // the HR feature map of a sub-chunk streams through HBM; long head launches amortise their prologue
     if (const char* e = getenv("FSR_HR_SUB")) hr_sub_ = std::max(1, atoi(e));
+    if (const char* e = getenv("FSR_CHUNK")) chunk_tiles_ = std::max(1, atoi(e));
     tc_prepare(weights);
   }
 }
@@ -94,6 +96,11 @@ Engine::~Engine() {
                        &d_in_depth, &d_in_dem, &d_out, &d_tmp_a, &d_tmp_b})
     b->release();
   win.release();
+  d_halo[0].release();
+  d_halo[1].release();
+  if (s_comp) cudaStreamDestroy(s_comp);
+  if (s_in) cudaStreamDestroy(s_in);
+  if (s_out) cudaStreamDestroy(s_out);
 }
 
 int64_t Engine::macs_per_tile() const {
@@ -113,7 +120,7 @@ int64_t Engine::macs_per_tile() const {
 
 void Engine::ensure_arena(int n_tiles) {
   if (n_tiles <= cap_tiles_) return;
-  const int cap = std::max(n_tiles, chunk_tiles_);
+  const int cap = std::min(ceil_div(n_tiles, 64) * 64, std::max(chunk_tiles_, n_tiles));  // grow-only, in steps of 64 tiles
   size_t headmid = 0;
   const size_t hr_px0 = (size_t)hdr_.hr_tile * hdr_.hr_tile, lr_px0 = (size_t)hdr_.lr_tile * hdr_.lr_tile;
   if (precision_ != FSR_PREC_FP32) {
@@ -359,18 +366,23 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
     e.d_stats.ensure((size_t)n_tiles * 3 * sizeof(float));
     stats = e.d_stats.as<float>();
   }
-  // origins local to the band's rows
   TileGrid grid;
-  std::vector<int> org((size_t)n_tiles * 2);
-  for (int yi = ty0; yi < ty1; ++yi)
-    for (int xi = 0; xi < nx; ++xi) {
-      org[((size_t)(yi - ty0) * nx + xi) * 2 + 0] = e.win.ys[yi] - band_row0;
-      org[((size_t)(yi - ty0) * nx + xi) * 2 + 1] = e.win.xs[xi];
-    }
-  e.d_tmp_a.ensure(org.size() * sizeof(int));
-  FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-  FSR_CUDA(cudaStreamSynchronize(s));
-  grid.origins = e.d_tmp_a.as<int2>();
+  if (band_row0 == 0) {
+    // the buffers hold the raster from its first row: the global window origins uploaded by setup_windows apply
+    grid.origins = e.win.d_origins.as<int2>() + (size_t)ty0 * nx;
+  } else {
+    // origins local to the band's rows
+    std::vector<int> org((size_t)n_tiles * 2);
+    for (int yi = ty0; yi < ty1; ++yi)
+      for (int xi = 0; xi < nx; ++xi) {
+        org[((size_t)(yi - ty0) * nx + xi) * 2 + 0] = e.win.ys[yi] - band_row0;
+        org[((size_t)(yi - ty0) * nx + xi) * 2 + 1] = e.win.xs[xi];
+      }
+    e.d_tmp_a.ensure(org.size() * sizeof(int));
+    FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    FSR_CUDA(cudaStreamSynchronize(s));
+    grid.origins = e.d_tmp_a.as<int2>();
+  }
   grid.H = std::min(e.win.H - band_row0, band_rows_hr);
   grid.W = e.win.W;
   grid.Hl = ceil_div(grid.H, e.scale());
@@ -532,18 +544,65 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   check_params(params, T * T);
   const int Hl = H / sc, Wl = W / sc;
   FSR_REQUIRE(Hl > 0 && Wl > 0, "raster smaller than one low-resolution cell");
-  cudaStream_t s = 0;
-  e.setup_windows(H, W, window_method, overlap_hr, y_starts, ny, x_starts, nx, ramp, s);
+  // Software pipeline over bands of window rows: the H2D copy of the rows band b+1 reads, the kernels of band b and
+  // the D2H copy of the rows band b-1 owns run on three streams.  Bands hand their shared rows over as partial
+  // sums exactly like ranks do (fsr_band_*), so the result is bit-identical to a single pass.  Copies only overlap
+  // when the host buffers are page-locked (fsr_host_alloc); pageable buffers work but serialise.
+  e.ensure_streams();
+  cudaStream_t sc_ = e.s_comp, si = e.s_in, so = e.s_out;
+  e.setup_windows(H, W, window_method, overlap_hr, y_starts, ny, x_starts, nx, ramp, sc_);
   e.d_in_depth.ensure((size_t)Hl * Wl * sizeof(float));
   e.d_in_dem.ensure((size_t)H * W * sizeof(float));
   e.d_out.ensure((size_t)H * W * sizeof(float));
-  FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, (size_t)Hl * Wl * sizeof(float), cudaMemcpyHostToDevice, s));
-  FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, dem_hr, (size_t)H * W * sizeof(float), cudaMemcpyHostToDevice, s));
-  band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), 0, H, 0, ny, *params, nullptr, nullptr, s);
-  band_finalize(e, nullptr, 0, e.d_out.as<float>(), s);
-  FSR_CUDA(cudaMemcpyAsync(out_sr, e.d_out.p, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)ny * nx * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-  unsigned f = e.fetch_flags(s);
+  e.d_stats.ensure((size_t)ny * nx * 3 * sizeof(float));
+  // band size: enough windows per band to keep the batched layer kernels efficient, small enough to overlap copies
+  int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
+  if (ny <= rows_per_band) rows_per_band = ny;
+  const int n_bands = ceil_div(ny, rows_per_band);
+  e.d_halo[0].ensure((size_t)T * W * sizeof(float));
+  e.d_halo[1].ensure((size_t)T * W * sizeof(float));
+  std::vector<cudaEvent_t> ev_in(n_bands), ev_done(n_bands);
+  for (int b = 0; b < n_bands; ++b) {
+    FSR_CUDA(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
+    FSR_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+  }
+  struct EvGuard {
+    std::vector<cudaEvent_t>&a, &b;
+    ~EvGuard() {
+      for (auto x : a) cudaEventDestroy(x);
+      for (auto x : b) cudaEventDestroy(x);
+    }
+  } guard{ev_in, ev_done};
+  // all input copies are queued up front, in band order
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, (size_t)Hl * Wl * sizeof(float), cudaMemcpyHostToDevice, si));
+  int copied = 0;
+  for (int b = 0; b < n_bands; ++b) {
+    const int ty1 = std::min((b + 1) * rows_per_band, (int)ny);
+    const int need = b == n_bands - 1 ? H : std::min(e.win.ys[ty1 - 1] + T, (int)H);
+    if (need > copied) {
+      FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.as<float>() + (size_t)copied * W, dem_hr + (size_t)copied * W,
+                               (size_t)(need - copied) * W * sizeof(float), cudaMemcpyHostToDevice, si));
+      copied = need;
+    }
+    FSR_CUDA(cudaEventRecord(ev_in[b], si));
+  }
+  for (int b = 0; b < n_bands; ++b) {
+    const int ty0 = b * rows_per_band, ty1 = std::min(ty0 + rows_per_band, (int)ny);
+    FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[b], 0));
+    band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), 0, H, ty0, ty1, *params, e.d_halo[b & 1].as<float>(),
+             e.d_stats.as<float>() + (size_t)ty0 * nx * 3, sc_);
+    const int halo_in = b == 0 ? 0 : e.band_halo_rows[(b - 1) & 1];
+    e.band_halo_rows[b & 1] = e.band.halo_out_rows;
+    band_finalize(e, b == 0 ? nullptr : e.d_halo[(b - 1) & 1].as<float>(), halo_in, e.d_out.as<float>() + (size_t)e.band.row0 * W, sc_);
+    FSR_CUDA(cudaEventRecord(ev_done[b], sc_));
+    FSR_CUDA(cudaStreamWaitEvent(so, ev_done[b], 0));
+    if (e.band.n_rows > 0)
+      FSR_CUDA(cudaMemcpyAsync(out_sr + (size_t)e.band.row0 * W, e.d_out.as<float>() + (size_t)e.band.row0 * W,
+                               (size_t)e.band.n_rows * W * sizeof(float), cudaMemcpyDeviceToHost, so));
+  }
+  if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)ny * nx * 3 * sizeof(float), cudaMemcpyDeviceToHost, sc_));
+  unsigned f = e.fetch_flags(sc_);
+  FSR_CUDA(cudaStreamSynchronize(so));
   if (out_flags) *out_flags = f;
   if (f) throw Error(FSR_E_ASSERT, "input validation failed on the device (see flags)");
   FSR_API_END()

@@ -130,6 +130,18 @@ class Engine {
   DeviceBuf d_stats;      // [n_tiles][3]
   DeviceBuf d_in_depth, d_in_dem, d_out;  // staging for the host-buffer entry points
   DeviceBuf d_tmp_a, d_tmp_b;
+  // fsr_run_raster pipeline: compute / H2D / D2H streams and the two hand-over buffers for rows shared by
+  // consecutive bands
+  cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
+  DeviceBuf d_halo[2];
+  int band_halo_rows[2] = {0, 0};
+  void ensure_streams() {
+    if (s_comp) return;
+    FSR_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    FSR_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    FSR_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  }
+  int band_tiles_target() const { return band_tiles_; }
 
  private:
   void ensure_arena(int n_tiles);
@@ -153,6 +165,7 @@ class Engine {
   int cap_tiles_ = 0;            // arena capacity (tiles per chunk)
   int hr_sub_ = 4;               // tiles per HR sub-chunk (tensor-core modes: 32; env FSR_HR_SUB overrides)
   int chunk_tiles_ = 64;
+  int band_tiles_ = 192;         // windows per band of the fsr_run_raster copy/compute pipeline (env FSR_BAND_TILES)
   DeviceBuf d_weights_, d_flags_, d_headmid_;
   std::vector<DeviceBuf> tbuf_;
   std::vector<float*> tbase_;    // per-forward tensor base pointers (inputs/outputs alias caller buffers)
