@@ -86,6 +86,7 @@ struct TcOp {
   DeviceBuf wpack;         // bf16 weights in the streaming layout of the op's kernel
   DeviceBuf packbuf;       // CP8 staging tensor for convs fed by 1-channel fp32 rasters
   bool pack_small = false;
+  bool rows = false;       // runs the persistent row-box conv kernel
   int kc = 0, C0 = 0, C1 = 0;
   std::vector<float> h_wdem, h_bias, h_w2;  // head epilogue constants (passed as kernel parameters)
   float h_b2 = 0.f;

@@ -1,6 +1,7 @@
 // FSR_PREC_BF16 backend of the Engine: tensor formats, weight packing and op dispatch onto the tcgen05 kernels.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -15,6 +16,11 @@ int conv_tc_bn(int cout);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, cudaStream_t s);
+bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc);
+void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
+                         const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
+                         long long plane_out, int n_img, int H, int W, int cout, int act, float alpha, int half, int n_sms,
+                         cudaStream_t s);
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
                        int chunks, int half, cudaStream_t s);
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
@@ -100,10 +106,19 @@ void Engine::tc_prepare(const float* w) {
         if (kc % 2) throw Error(FSR_E_UNSUPPORTED, "bf16 backend: conv input channels must be multiples of 16");
         kc /= 2;
       }
+      {
+        // wide, shallow levels run the persistent row-box kernel, which works on 32-channel groups
+        const auto& d = tensors_[op.dst];
+        const int kc_rows = kc > 4 ? 4 : kc;
+        if (!getenv("FSR_NO_CONV_ROWS") && conv_rows_ok(d.h, d.w, op.k, op.cout, C0, C1, kc_rows)) {
+          kc = kc_rows;
+          t.rows = true;
+        }
+      }
       t.kc = kc;
       t.C0 = C0;
       t.C1 = C1;
-      const int BN = conv_tc_bn(op.cout);
+      const int BN = t.rows ? op.cout : conv_tc_bn(op.cout);
       const int n_tiles = ceil_div(op.cout, BN);
       const int taps = op.k * op.k;
       const int s0 = (C0 / 8) / kc, s1 = C1 ? (C1 / 8) / kc : 0;
@@ -250,8 +265,12 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
             pl1 = tc_plane(op.src1);
           }
         }
-        launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
-                       tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, s);
+        if (tc.rows)
+          launch_conv_rows_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res),
+                              cp8(op.dst), tc_plane(op.dst), n, td.h, td.w, op.cout, op.act, op.alpha, half, n_sms_, s);
+        else
+          launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
+                         tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, s);
         break;
       }
       case FSR_OP_POOL:

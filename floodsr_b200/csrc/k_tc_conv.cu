@@ -45,10 +45,12 @@ template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int kABytesMax = 8 * 128 * 16;
-  constexpr int kBBytesMax = 8 * BN * 16;
-  uint8_t* smem_a = smem_raw;                                   // kStages x kABytesMax
-  uint8_t* smem_b = smem_raw + kStages * kABytesMax;            // kStages x kBBytesMax
+  // stages are sized for this layer's K slice (kc 8-channel planes), so narrow layers fit several CTAs per SM and
+  // their TMA latencies overlap
+  const int kABytesMax = p.kc * 128 * 16;
+  const int kBBytesMax = p.kc * BN * 16;
+  uint8_t* smem_a = smem_raw;                                   // kStages x a_bytes
+  uint8_t* smem_b = smem_raw + kStages * kABytesMax;            // kStages x b_bytes
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * kBBytesMax);
   uint64_t* full = bars;                // [kStages]
   uint64_t* empty = bars + kStages;     // [kStages]
@@ -183,6 +185,187 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 }
 
+
+// ---- persistent row-box variant for the wide, shallow levels ------------------------------------------------------
+// For 3x3 layers whose M tile (128 pixels = bh whole image rows of width bw == W) lies inside one image and whose
+// packed weights fit in shared memory.  One CTA per SM loops over M tiles:
+//   * the weights are loaded once per CTA;
+//   * per (M tile, 32-channel group) only THREE halo boxes are fetched (dx = -1, 0, +1; bh + 2 rows each): the dy taps
+//     are row offsets (bw * 16 B) into a box, so the L2 -> shared-memory traffic is 3 boxes instead of 9;
+//   * accumulators are double-buffered in TMEM, so the epilogue of tile t overlaps the MMAs of tile t + 1, and the
+//     per-CTA set-up (TMEM allocation, barrier init, first TMA latency) is paid once per SM instead of once per tile.
+constexpr int kRowStages = 3;
+
+struct ConvRowsParams {
+  int H, W, N;
+  int bw, bh;          // bw == W, bw * bh == 128
+  int tiles_per_img;   // H / bh
+  int n_mtiles;        // N * tiles_per_img
+  int kc;              // 8-channel planes per channel group (2 or 4)
+  int g0, g1;          // channel groups coming from src0 / src1
+  int cout, act;
+  float alpha;
+  int half;
+  long long plane;     // pixels per CP8 plane of the output/residual tensors
+  const __nv_bfloat16* wpack;  // [tap][group][kc][BN][8]
+  int w_bytes;
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* out;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvRowsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int plane_b = (p.bh + 2) * p.bw * 16;       // one 8-channel plane of a halo box
+  const int dx_bytes = p.kc * plane_b;               // one box
+  const int w_round = (p.w_bytes + 1023) & ~1023;
+  uint8_t* smem_w = smem_raw;
+  uint8_t* smem_a = smem_raw + w_round;              // kRowStages x 3 boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kRowStages * 3 * dx_bytes);
+  uint64_t* w_full = bars;
+  uint64_t* full = bars + 1;                 // [kRowStages]
+  uint64_t* empty = full + kRowStages;       // [kRowStages]
+  uint64_t* acc_full = empty + kRowStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = p.g0 + p.g1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.g1 > 0) tma_prefetch_desc(&tmA1);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(w_full, 1);
+      for (int i = 0; i < kRowStages; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&acc_full[i], 1);
+        mbar_init(&acc_empty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)p.w_bytes);
+      bulk_load_1d(smem_w, p.wpack, (uint32_t)p.w_bytes, w_full);
+      int it = 0;
+      for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+        const int img = mt / p.tiles_per_img, ty = mt % p.tiles_per_img;
+        for (int g = 0; g < groups; ++g, ++it) {
+          const int s = it % kRowStages;
+          mbar_wait(&empty[s], ((it / kRowStages) & 1) ^ 1);
+          mbar_expect_tx(&full[s], 3u * (uint32_t)dx_bytes);
+          const bool second = g >= p.g0;
+          const CUtensorMap* tm = second ? &tmA1 : &tmA0;
+          const int chunk0 = (second ? g - p.g0 : g) * p.kc;
+          for (int dxi = 0; dxi < 3; ++dxi)
+            tma_load_5d(smem_a + (s * 3 + dxi) * dx_bytes, tm, &full[s], 0, dxi - 1, ty * p.bh - 1, img, chunk0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = idesc_16(128, BN, p.half);
+    mbar_wait(w_full, 0);
+    const uint64_t da_base = smem_desc_kmajor(smem_u32(smem_a), (uint32_t)plane_b, 128);
+    const uint64_t db_base = smem_desc_kmajor(smem_u32(smem_w), BN * 16, 128);
+    const int kpairs = p.kc / 2;
+    int it = 0, nt = 0;
+    for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++nt) {
+      const int ab = nt & 1;
+      mbar_wait(&acc_empty[ab], ((nt >> 1) & 1) ^ 1);
+      const uint32_t d = tmem_base + ab * BN;
+      for (int g = 0; g < groups; ++g, ++it) {
+        const int s = it % kRowStages;
+        mbar_wait(&full[s], (it / kRowStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap % 3;
+            const uint64_t da = da_base + (uint64_t)(((s * 3 + kx) * dx_bytes + ky * p.bw * 16) >> 4);
+            const uint64_t db = db_base + (uint64_t)((((tap * groups + g) * p.kc) * BN * 16) >> 4);
+            for (int j = 0; j < kpairs; ++j)
+              umma_bf16(d, da + (uint64_t)((j * 2 * plane_b) >> 4), db + (uint64_t)((j * 2 * BN * 16) >> 4), idesc,
+                        (g > 0 || tap > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (g == groups - 1) umma_commit(&acc_full[ab]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int lx = m % p.bw, ly = m / p.bw;
+    int nt = 0;
+    for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++nt) {
+      const int ab = nt & 1;
+      const int img = mt / p.tiles_per_img, ty = mt % p.tiles_per_img;
+      const long long pix = ((long long)img * p.H + (ty * p.bh + ly)) * p.W + lx;
+      mbar_wait(&acc_full[ab], (nt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN;
+#pragma unroll
+      for (int c32 = 0; c32 < BN / 32; ++c32) {
+        float v[32];
+        tmem_ld32(taddr + c32 * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int co = c32 * 32 + c * 8;
+          const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = v[c * 8 + i];
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
+            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+            o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+          }
+          if (p.res) {
+            float r[8];
+            unpack_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), r, p.half);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += r[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = apply_act(o[i], p.act, p.alpha);
+          *reinterpret_cast<uint4*>(p.out + off) = pack_x8(o, p.half);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // ---- CP8 helper kernels (memory-bound, 16-byte vectors) -----------------------------------------------------
 
 // concat of up to two 1-channel fp32 NHWC tensors -> CP8 bf16 with `chunks` 8-channel planes (zero padded)
@@ -308,8 +491,8 @@ inline int grid_for(long long total, int threads = 256) {
 }
 
 template <int BN>
-size_t conv_smem_bytes() {
-  return (size_t)kStages * (8 * 128 * 16) + (size_t)kStages * (8 * BN * 16) + (2 * kStages + 1) * sizeof(uint64_t) + 16;
+size_t conv_smem_bytes(int kc) {
+  return (size_t)kStages * (kc * 128 * 16) + (size_t)kStages * (kc * BN * 16) + (2 * kStages + 1) * sizeof(uint64_t) + 16;
 }
 
 }  // namespace
@@ -398,16 +581,59 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)ceil_div(cout, BN));
   if (BN == 128) {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<128>())); attr = true; }
-    conv_tc_kernel<128><<<grid, kConvThreads, conv_smem_bytes<128>(), s>>>(m0, m1, p);
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<128>(8))); attr = true; }
+    conv_tc_kernel<128><<<grid, kConvThreads, conv_smem_bytes<128>(kc), s>>>(m0, m1, p);
   } else if (BN == 64) {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<64>())); attr = true; }
-    conv_tc_kernel<64><<<grid, kConvThreads, conv_smem_bytes<64>(), s>>>(m0, m1, p);
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<64>(8))); attr = true; }
+    conv_tc_kernel<64><<<grid, kConvThreads, conv_smem_bytes<64>(kc), s>>>(m0, m1, p);
   } else {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<32>())); attr = true; }
-    conv_tc_kernel<32><<<grid, kConvThreads, conv_smem_bytes<32>(), s>>>(m0, m1, p);
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<32>(8))); attr = true; }
+    conv_tc_kernel<32><<<grid, kConvThreads, conv_smem_bytes<32>(kc), s>>>(m0, m1, p);
+  }
+  FSR_LAUNCH_CHECK();
+}
+
+
+// Row-box variant: usable when an M tile is bh whole rows of one image and the packed weights fit in shared memory.
+bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc) {
+  if (ksz != 3 || (W != 16 && W != 32) || (cout != 32 && cout != 64)) return false;
+  const int bh = 128 / W;
+  if (H % bh) return false;
+  if (kc != 2 && kc != 4) return false;
+  const size_t w_bytes = (size_t)9 * ((C0 + C1) / 8) * cout * 16;
+  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + (size_t)kRowStages * 3 * kc * (bh + 2) * W * 16 + 256;
+  return smem <= 200 * 1024;
+}
+
+void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
+                         const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
+                         long long plane_out, int n_img, int H, int W, int cout, int act, float alpha, int half, int n_sms,
+                         cudaStream_t s) {
+  ConvRowsParams p{};
+  p.H = H; p.W = W; p.N = n_img;
+  p.bw = W; p.bh = 128 / W;
+  p.tiles_per_img = H / p.bh;
+  p.n_mtiles = n_img * p.tiles_per_img;
+  p.kc = kc;
+  p.g0 = (C0 / 8) / kc;
+  p.g1 = src1 ? (C1 / 8) / kc : 0;
+  p.cout = cout; p.act = act; p.alpha = alpha; p.half = half;
+  p.plane = plane_out;
+  p.wpack = wpack;
+  p.w_bytes = 9 * (p.g0 + p.g1) * kc * cout * 16;
+  p.bias = bias; p.res = res; p.out = dst;
+  CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh + 2, 1, kc);
+  CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh + 2, 1, kc) : m0;
+  const size_t smem = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023) + (size_t)kRowStages * 3 * kc * (p.bh + 2) * W * 16 + 256;
+  const int grid = p.n_mtiles < n_sms ? p.n_mtiles : n_sms;
+  if (cout == 64) {
+    FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    conv_rows_tc_kernel<64><<<grid, kConvThreads, smem, s>>>(m0, m1, p);
+  } else {
+    FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    conv_rows_tc_kernel<32><<<grid, kConvThreads, smem, s>>>(m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
 }
