@@ -2,12 +2,15 @@
 // -> activation -> conv1x1 -> invert_depth_log1p.  ~81 % of the FLOPs behind `session.run`
 // (floodsr/engine/ort.py:193) plus the invert_depth_log1p_np call after it (ort.py:196, preprocessing.py:154-164).
 //
-// Persistent kernel, one CTA per SM.  The launch's output rows (128-pixel-wide strips of every tile, flattened)
-// are split into gridDim.x equal contiguous ranges, so every SM gets the same number of rows; a range is walked
-// as "items" = runs of rows inside one strip.
+// Persistent kernel, one CTA per SM running TWO independent row pipelines (8 warps each).  The launch's output
+// rows (128-pixel-wide strips of every tile, flattened) are split into 2 * gridDim.x equal contiguous ranges, one
+// per pipeline, so every SM gets the same number of rows; a range is walked as "items" = runs of rows inside one
+// strip.  A single MMA-issuing warp cannot keep the tensor core busy at N = 96 (its per-row barrier polls and
+// descriptor arithmetic take longer than the queued MMAs), so two issuers feed it alternately, each into its own
+// half of TMEM; MMAs of one pipeline stay ordered, which keeps the result deterministic.
 //
-// TMEM holds a ring of 16 output-row accumulators D_y[x, co] (128 lanes x 32 fp32 columns each = all 512
-// columns).  An *input* row r feeds the three output rows y = r+1, r, r-1 (ky = 0, 1, 2) with ONE N = 96 MMA per
+// Per pipeline, TMEM holds a ring of 8 output-row accumulators D_y[x, co] (128 lanes x 32 fp32 columns each; both
+// rings together = all 512 columns).  An *input* row r feeds the three output rows y = r+1, r, r-1 (ky = 0, 1, 2) with ONE N = 96 MMA per
 // K step, because their accumulators are adjacent in the ring and the weight operand is stored
 // [ky = 2 | ky = 1 | ky = 0] along N:
 //     D_{r-1} | D_r | D_{r+1}  +=  F[r, x + kx - 1, ci-slice] * [W(2,kx) | W(1,kx) | W(0,kx)]     (6 K steps)
@@ -21,8 +24,8 @@
 // When input row y+1 has been issued, D_y is complete: the epilogue reads its 32 columns once, applies the
 // activation, the 1x1 projection and the log1p inversion in fp32 and stores coalesced rows.
 //
-// Warp roles: 0 TMA producer | 1 MMA issuer | 2 DEM prefetcher | 3 DEM-operand builder | 4.. epilogue groups
-// (4 warps each, output rows alternate between groups).  All hand-offs are mbarriers.
+// Warp roles per pipeline: 0 TMA producer | 1 MMA issuer | 2 DEM prefetcher | 3 DEM-operand builder | 4-7 epilogue
+// (one warp per TMEM lane quarter).  All hand-offs are mbarriers.
 #include <stdlib.h>
 
 #include "fsr_engine.cuh"
@@ -38,8 +41,9 @@ namespace {
 
 constexpr int kCmid = 32;
 constexpr int kNfull = 3 * kCmid;                 // widest MMA: three adjacent output-row accumulators
-constexpr int kSlots = 16;                        // 16 x 32 fp32 columns = the whole TMEM
-constexpr int kStages = 18;                       // input rows in flight per SM: ~150 KB, sized for HBM latency
+constexpr int kPipes = 2;                         // independent row pipelines per CTA (each with its own MMA-issuing warp)
+constexpr int kSlots = 8;                         // accumulator ring per pipeline: 8 x 32 fp32 columns = half the TMEM
+constexpr int kStages = 9;                        // input rows in flight per pipeline (18 per SM, ~150 KB: HBM latency)
 constexpr int kRowPx = 130;                       // 128 + left/right halo pixel
 constexpr int kPlaneBytes = kRowPx * 16;          // 2080
 constexpr int kRowBytes = 4 * kPlaneBytes;        // 32 feature channels = 4 planes
@@ -48,9 +52,9 @@ constexpr int kWBytes = 6 * kWStep;               // (kx, k-slice)
 constexpr int kW2Bytes = kWStep;                  // DEM/bias operand
 constexpr int kA2Bytes = 128 * 16;                // DEM operand plane per stage
 constexpr int kDemBytes = 640;                    // per-stage fp32 DEM halo row (128-byte aligned)
-constexpr int kEpiGroups = 2;
-constexpr int kThreads = 128 + 128 * kEpiGroups;
-constexpr int kSmemBytes = kWBytes + kW2Bytes + kStages * (kRowBytes + kA2Bytes + kDemBytes) + kA2Bytes + 1024;  // one CTA per SM
+constexpr int kPipeThreads = 256;                 // producer, MMA, DEM prefetch, DEM builder, 4 epilogue warps
+constexpr int kThreads = kPipes * kPipeThreads;
+constexpr int kSmemBytes = kWBytes + kW2Bytes + kPipes * kStages * (kRowBytes + kA2Bytes + kDemBytes) + kA2Bytes + 2048;  // one CTA per SM
 
 struct HeadParams {
   int H, W, N;          // HR tile extent and tiles in this launch
@@ -104,9 +108,10 @@ struct ItemIter {
   long long r, r_end;
   int H, segs;
   int img, xs, y0, rows;
-  __device__ ItemIter(const HeadParams& p) : H(p.H), segs(p.W / 128) {
-    r = p.total_rows * (long long)blockIdx.x / gridDim.x;
-    r_end = p.total_rows * (long long)(blockIdx.x + 1) / gridDim.x;
+  __device__ ItemIter(const HeadParams& p, int pipe) : H(p.H), segs(p.W / 128) {
+    const long long vb = (long long)blockIdx.x * kPipes + pipe, nvb = (long long)gridDim.x * kPipes;
+    r = p.total_rows * vb / nvb;
+    r_end = p.total_rows * (vb + 1) / nvb;
   }
   __device__ bool next() {
     if (r >= r_end) return false;
@@ -168,35 +173,44 @@ template <int ACT, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ HeadParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem_w = smem_raw;                                   // 18432 B
+  const int warp_abs = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = warp_abs >> 3;     // pipeline of this warp
+  const int warp = warp_abs & 7;   // role inside the pipeline
+  uint8_t* smem_w = smem_raw;                                   // 18432 B (shared by both pipelines)
   uint8_t* smem_w2 = smem_w + kWBytes;                          // 3072 B
-  uint8_t* smem_rows = smem_w2 + kW2Bytes;                      // kStages x 8320 B (128-B aligned)
-  uint8_t* smem_a2 = smem_rows + kStages * kRowBytes;           // kStages x 2048 B
-  uint8_t* smem_zero = smem_a2 + kStages * kA2Bytes;            // 2048 B of zeros: upper K plane of every DEM operand
-  uint8_t* smem_dem = smem_zero + kA2Bytes;                     // kStages x 640 B fp32 DEM halo rows
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dem + kStages * kDemBytes);
+  uint8_t* smem_rows_all = smem_w2 + kW2Bytes;                  // kPipes x kStages x 8320 B (128-B aligned)
+  uint8_t* smem_a2_all = smem_rows_all + kPipes * kStages * kRowBytes;   // kPipes x kStages x 2048 B
+  uint8_t* smem_zero = smem_a2_all + kPipes * kStages * kA2Bytes;        // 2048 B of zeros: upper K plane of every DEM operand
+  uint8_t* smem_dem_all = smem_zero + kA2Bytes;                 // kPipes x kStages x 640 B fp32 DEM halo rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dem_all + kPipes * kStages * kDemBytes);
+  constexpr int kBarsPerPipe = 3 * kStages + 2 * kSlots;
   uint64_t* w_full = bars;
-  uint64_t* row_full = bars + 1;                 // [kStages]  TMA bytes + DEM builder arrival -> MMA
+  uint64_t* pbars = bars + 1 + v * kBarsPerPipe;
+  uint64_t* row_full = pbars;                    // [kStages]  TMA bytes + DEM builder arrival -> MMA
   uint64_t* row_empty = row_full + kStages;      // [kStages]  MMA -> producers
   uint64_t* dem_full = row_empty + kStages;      // [kStages]  DEM prefetcher (32 cp.async arrivals) -> builder
   uint64_t* slot_full = dem_full + kStages;      // [kSlots]   MMA -> epilogue
   uint64_t* slot_empty = slot_full + kSlots;     // [kSlots]   epilogue (4 warps) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + kSlots);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + kPipes * kBarsPerPipe);
+  uint8_t* smem_rows = smem_rows_all + v * kStages * kRowBytes;
+  uint8_t* smem_a2 = smem_a2_all + v * kStages * kA2Bytes;
+  uint8_t* smem_dem = smem_dem_all + v * kStages * kDemBytes;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmF);
-  if (warp == 1) {
+  if (warp_abs == 0 && lane == 0) tma_prefetch_desc(&tmF);
+  if (warp_abs == 1) {
     if (lane == 0) {
       mbar_init(w_full, 1);
-      for (int i = 0; i < kStages; ++i) {
-        mbar_init(&row_full[i], 2);
-        mbar_init(&row_empty[i], 1);
-        mbar_init(&dem_full[i], 32);
-      }
-      for (int i = 0; i < kSlots; ++i) {
-        mbar_init(&slot_full[i], 1);
-        mbar_init(&slot_empty[i], 4);
+      for (int pp = 0; pp < kPipes; ++pp) {
+        uint64_t* b = bars + 1 + pp * kBarsPerPipe;
+        for (int i = 0; i < kStages; ++i) {
+          mbar_init(&b[i], 2);                       // row_full
+          mbar_init(&b[kStages + i], 1);             // row_empty
+          mbar_init(&b[2 * kStages + i], 32);        // dem_full
+        }
+        for (int i = 0; i < kSlots; ++i) {
+          mbar_init(&b[3 * kStages + i], 1);         // slot_full
+          mbar_init(&b[3 * kStages + kSlots + i], 4);  // slot_empty
+        }
       }
       fence_barrier_init();
     }
@@ -204,15 +218,16 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp == 2) {
+  if (warp_abs == 2) {
     for (int i = lane; i < kA2Bytes / 16; i += 32) reinterpret_cast<uint4*>(smem_zero)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 4 && warp < 8) {
+  const uint32_t tmem_alloc_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_alloc_base + v * (kSlots * kCmid);  // this pipeline's half of the accumulator columns
+  if (warp >= 4) {
     // every MMA accumulates: start from zeroed accumulators (the epilogue re-zeroes a slot after reading it)
     for (int sl = 0; sl < kSlots; ++sl) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + sl * kCmid);
     tmem_st_wait();
@@ -224,11 +239,13 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one halo row per input row ===================
     if (lane == 0) {
-      mbar_expect_tx(w_full, kWBytes + kW2Bytes);
-      bulk_load_1d(smem_w, p.wpack, kWBytes + kW2Bytes, w_full);
+      if (v == 0) {
+        mbar_expect_tx(w_full, kWBytes + kW2Bytes);
+        bulk_load_1d(smem_w, p.wpack, kWBytes + kW2Bytes, w_full);
+      }
       int g = 0, s = 0;  // running input-row counter of this CTA and its smem stage
       uint32_t ph = 1;
-      for (ItemIter it(p); it.next();) {
+      for (ItemIter it(p, v); it.next();) {
         const int n_in = it.rows + 2;
         for (int i = 0; i < n_in; ++i, ++g) {
           mbar_wait_relaxed(&row_empty[s], ph);
@@ -237,7 +254,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
-      if (STATS && p.stats && blockIdx.x == 0) p.stats[2] = g;
+      if (STATS && p.stats && blockIdx.x == 0 && v == 0) p.stats[2] = g;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================================================================
@@ -263,7 +280,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     uint32_t sph = 0, a = a_lo0, a2 = a2_lo0, bar_full = bar_full0, bar_empty = bar_empty0;
     int go = 0;           // output rows of earlier items
     long long c_se = 0, c_rf = 0, t0 = STATS ? clock64() : 0;
-    for (ItemIter it(p); it.next(); go += it.rows) {
+    for (ItemIter it(p, v); it.next(); go += it.rows) {
       const int n_in = it.rows + 2;
       for (int i = 0; i < n_in; ++i) {
         const int R = go + i;  // ring index of the output row this input row opens (ky = 0)
@@ -325,14 +342,14 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
       }
     }
     (void)bar_full; (void)bar_slot_empty;
-    if (STATS && p.stats && blockIdx.x == 0 && lane == 0) { p.stats[3] = c_se; p.stats[4] = c_rf; p.stats[5] = 0; p.stats[6] = clock64() - t0; }
+    if (STATS && p.stats && blockIdx.x == 0 && v == 0 && lane == 0) { p.stats[3] = c_se; p.stats[4] = c_rf; p.stats[5] = 0; p.stats[6] = clock64() - t0; }
   } else if (warp == 2) {
     // ===================== DEM prefetcher: fp32 halo rows -> smem, up to kStages rows ahead =================
     // 4-byte cp.async (zero-filled outside the tile); completion is signalled straight to the builder's mbarrier,
     // so this warp never waits for memory.
     int s = 0;
     uint32_t ph = 1;
-    for (ItemIter it(p); it.next();) {
+    for (ItemIter it(p, v); it.next();) {
       const int n_in = it.rows + 2;
       for (int i = 0; i < n_in; ++i) {
         const int y = it.y0 - 1 + i;
@@ -355,7 +372,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     const uint32_t ones = (uint32_t)to16(1.0f, p.half) * 0x10001u;
     int s = 0;
     uint32_t ph = 0;
-    for (ItemIter it(p); it.next();) {
+    for (ItemIter it(p, v); it.next();) {
       const int n_in = it.rows + 2;
       for (int i = 0; i < n_in; ++i) {
         mbar_wait_relaxed(&dem_full[s], ph);
@@ -384,8 +401,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue groups: each finished accumulator is read exactly once =================
-    const int grp = (warp - 4) >> 2;
+    // ===================== epilogue: each finished accumulator is read exactly once ========================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -394,11 +410,10 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     for (int c = 0; c < kCmid; ++c) w2r[c] = p.w2[c];
     int go = 0;
     long long c_sf = 0, t0 = STATS ? clock64() : 0;
-    for (ItemIter it(p); it.next(); go += it.rows) {
+    for (ItemIter it(p, v); it.next(); go += it.rows) {
       const int x = it.xs * 128 + m;
       for (int j = 0; j < it.rows; ++j) {
         const int r = go + j;
-        if ((r % kEpiGroups) != grp) continue;
         const int slot = r & (kSlots - 1);
         if (STATS) mbar_wait_t<STATS>(&slot_full[slot], (r / kSlots) & 1, c_sf); else mbar_wait_relaxed(&slot_full[slot], (r / kSlots) & 1);
         tc_fence_after();
@@ -428,9 +443,9 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     if (p.stats && blockIdx.x == 0 && warp == 4 && lane == 0) { p.stats[7] = c_sf; p.stats[8] = clock64() - t0; }
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp_abs == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_alloc_base, 512);
   }
 }
 
