@@ -64,6 +64,14 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
     producer[op.dst] = (int)i;
   }
 
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    const fsr_op& op = ops_[i];
+    if (op.kind == FSR_OP_POOL && op.src0 == 1 && op.mode == 1 && op.k == hdr_.scale && hdr_.scale == 16 && hdr_.hr_tile == 512 &&
+        tensors_[op.dst].c == 1) {
+      pooled_op_ = (int)i;  // the normalisation kernel produces this tensor on the fly
+      break;
+    }
+  }
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev <= 0)
@@ -92,7 +100,7 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
 Engine::~Engine() {
   cudaSetDevice(device_);
   for (auto& b : tbuf_) b.release();
-  for (DeviceBuf* b : {&d_weights_, &d_flags_, &d_headmid_, &d_dem_norm_, &d_depth_norm_, &d_pred_norm_, &d_tiles, &d_stats,
+  for (DeviceBuf* b : {&d_weights_, &d_flags_, &d_headmid_, &d_dem_norm_, &d_depth_norm_, &d_pred_norm_, &d_dem_lr_, &d_tiles, &d_stats,
                        &d_in_depth, &d_in_dem, &d_out, &d_tmp_a, &d_tmp_b})
     b->release();
   win.release();
@@ -128,6 +136,7 @@ void Engine::ensure_arena(int n_tiles) {
     d_dem_norm_.ensure(hr_px0 * sizeof(float) * cap);
     d_pred_norm_.ensure(hr_px0 * sizeof(float) * cap);
     d_depth_norm_.ensure(lr_px0 * sizeof(float) * cap);
+    d_dem_lr_.ensure(lr_px0 * sizeof(float) * cap);
     cap_tiles_ = cap;
     return;
   }
@@ -147,6 +156,7 @@ void Engine::ensure_arena(int n_tiles) {
   d_dem_norm_.ensure(hr_px * sizeof(float) * cap);
   d_pred_norm_.ensure(hr_px * sizeof(float) * cap);
   d_depth_norm_.ensure(lr_px * sizeof(float) * cap);
+  d_dem_lr_.ensure(lr_px * sizeof(float) * cap);
   cap_tiles_ = cap;
 }
 
@@ -162,7 +172,7 @@ void Engine::run_ops(bool hr_phase, int n, int sub_start, cudaStream_t s) {
   const float* W = d_weights_.as<float>();
   auto wp = [&](int off) -> const float* { return off >= 0 ? W + off : nullptr; };
   for (size_t i = 0; i < ops_.size(); ++i) {
-    if ((op_hr_[i] != 0) != hr_phase) continue;
+    if ((op_hr_[i] != 0) != hr_phase || (int)i == skip_op_) continue;
     const fsr_op& op = ops_[i];
     const auto& ts = tensors_[op.src0];
     const auto& td = tensors_[op.dst];
@@ -212,6 +222,11 @@ void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_
     for (size_t i = 0; i < tensors_.size(); ++i) tbase_[i] = tbuf_[i].as<float>();
     tbase_[0] = const_cast<float*>(d_depth_norm) + (size_t)c0 * lr_px;
     tbase_[1] = const_cast<float*>(d_dem_norm) + (size_t)c0 * hr_px;
+    skip_op_ = -1;
+    if (dem_lr_pre_ && pooled_op_ >= 0) {
+      tbase_[ops_[pooled_op_].dst] = const_cast<float*>(dem_lr_pre_) + (size_t)c0 * lr_px;
+      skip_op_ = pooled_op_;
+    }
     float* pm = d_pred_m ? d_pred_m + (size_t)c0 * hr_px : nullptr;
     if (precision_ != FSR_PREC_FP32) {
       tbase_[hdr_.out_tensor] = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
@@ -242,10 +257,12 @@ void Engine::run_tiles_from_grid(const float* d_depth, const float* d_dem, const
     {
       ProfScope scope(prof, PROF_PROLOGUE, s);
       launch_tile_normalize(d_dem, d_depth, grid, tile_base + c0, n, T, TL, hdr_.scale, p, d_dem_norm_.as<float>(),
-                            d_depth_norm_.as<float>(), d_stats_out, d_flags(), s);
+                            d_depth_norm_.as<float>(), d_stats_out, d_dem_lr_.as<float>(), d_flags(), s);
     }
+    dem_lr_pre_ = p.normalize_inputs ? d_dem_lr_.as<float>() : nullptr;
     float* pn = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
     forward(n, d_depth_norm_.as<float>(), d_dem_norm_.as<float>(), pn, d_pred_m + (size_t)c0 * hr_px, p.max_depth, p.depth_denom, s);
+    dem_lr_pre_ = nullptr;
   }
 }
 
@@ -687,7 +704,7 @@ int fsr_stage_normalize(fsr_engine* eng, const float* depth_lr, const float* dem
   FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   TileGrid grid{e.d_tmp_a.as<int2>(), n_tiles * T, T, n_tiles * TL, TL};
   launch_tile_normalize(e.d_in_dem.as<float>(), e.d_in_depth.as<float>(), grid, 0, n_tiles, T, TL, e.scale(), *params,
-                        e.d_out.as<float>(), e.d_tmp_b.as<float>(), e.d_stats.as<float>(), e.d_flags(), s);
+                        e.d_out.as<float>(), e.d_tmp_b.as<float>(), e.d_stats.as<float>(), nullptr, e.d_flags(), s);
   if (out_depth_norm) FSR_CUDA(cudaMemcpyAsync(out_depth_norm, e.d_tmp_b.p, lr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (out_dem_norm) FSR_CUDA(cudaMemcpyAsync(out_dem_norm, e.d_out.p, hr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)n_tiles * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -47,7 +47,7 @@ struct DeviceBuf {
 // kernel launchers (k_prologue.cu, k_fp32.cu, k_blend.cu)
 void launch_tile_normalize(const float* d_dem, const float* d_depth, const TileGrid& grid, int tile_base, int n_tiles,
                            int T, int TL, int scale, const fsr_tile_params& p, float* d_dem_norm, float* d_depth_norm,
-                           float* d_stats, unsigned* d_flags, cudaStream_t stream);
+                           float* d_stats, float* d_dem_lr, unsigned* d_flags, cudaStream_t stream);
 void launch_conv_fp32(const float* src0, int C0, const float* src1, int C1, const float* w, const float* bias,
                       const float* res, float* dst, int n_img, int H, int W, int k, int cout, int act, float alpha,
                       cudaStream_t s);
@@ -170,7 +170,10 @@ class Engine {
   DeviceBuf d_weights_, d_flags_, d_headmid_;
   std::vector<DeviceBuf> tbuf_;
   std::vector<float*> tbase_;    // per-forward tensor base pointers (inputs/outputs alias caller buffers)
-  DeviceBuf d_dem_norm_, d_depth_norm_, d_pred_norm_;
+  DeviceBuf d_dem_norm_, d_depth_norm_, d_pred_norm_, d_dem_lr_;
+  const float* dem_lr_pre_ = nullptr;  // pooled normalised DEM written by the normalisation kernel for the current batch
+  int skip_op_ = -1;                   // op skipped by the current forward pass
+  int pooled_op_ = -1;                 // plan op it replaces (scale x scale average pool of the DEM input), or -1
 };
 
 }  // namespace fsr

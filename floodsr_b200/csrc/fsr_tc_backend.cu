@@ -237,7 +237,7 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
     return tbase_[tid] + (size_t)sub_start * t.h * t.w * t.c;
   };
   for (size_t i = 0; i < ops_.size(); ++i) {
-    if ((op_hr_[i] != 0) != hr_phase) continue;
+    if ((op_hr_[i] != 0) != hr_phase || (int)i == skip_op_) continue;
     const fsr_op& op = ops_[i];
     TcOp& tc = tc_ops_[i];
     const auto& ts = tensors_[op.src0];

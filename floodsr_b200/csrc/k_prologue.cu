@@ -18,9 +18,14 @@ namespace fsr {
 
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kThreads = 512;      // two CTAs per SM: one tile's barrier-heavy selection overlaps the other's streaming
 constexpr int kBins = 2048;
 constexpr int kDigitBits = 11;
+constexpr int kBinsPerThread = kBins / kThreads;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCap = 22528;        // compacted upper-tail keys kept in shared memory (88 KB)
+constexpr int kSampleStep = 8;     // every 8th float4 of the tile feeds the threshold estimate
+constexpr int kUnroll = 4;         // independent loads in flight per thread in the streaming passes
 
 struct SelState {
   unsigned lo, hi;  // inclusive key range still containing the wanted order statistic
@@ -56,13 +61,24 @@ __device__ __forceinline__ float4 load4(const float* __restrict__ dem, int H, in
   return v;
 }
 
-// Find, for `rank`, the histogram bin whose cumulative count first exceeds it.  All threads call this.
-// Result is published through smem (*sel_bin, *sel_before).
+// key of a DEM value: bit pattern of clip(fix(x), 0, inf) (+0.0f canonicalises -0.0), monotone in the value
+__device__ __forceinline__ unsigned dem_key(float x, const fsr_tile_params& p, unsigned& flags) {
+  return __float_as_uint(fmaxf(fix_dem(x, p, flags), 0.0f) + 0.0f);
+}
+
+// Exclusive prefix over the histogram; publishes (through smem) the bin whose cumulative count first exceeds `rank`
+// and the count before it.  All threads call this.
 __device__ void find_bin(const int* __restrict__ hist, int rank, int* warp_tot, int* sel_bin, int* sel_before) {
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
-  const int h0 = hist[2 * t], h1 = hist[2 * t + 1];
-  int incl = h0 + h1;
+  int h[kBinsPerThread];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < kBinsPerThread; ++k) {
+    h[k] = hist[kBinsPerThread * t + k];
+    sum += h[k];
+  }
+  int incl = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     int n = __shfl_up_sync(0xffffffffu, incl, o);
@@ -71,23 +87,24 @@ __device__ void find_bin(const int* __restrict__ hist, int rank, int* warp_tot, 
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    int w = warp_tot[lane];
+    int w = lane < kWarps ? warp_tot[lane] : 0;
     int s = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int n = __shfl_up_sync(0xffffffffu, s, o);
       if (lane >= o) s += n;
     }
-    warp_tot[lane] = s - w;  // exclusive prefix of warp totals
+    if (lane < kWarps) warp_tot[lane] = s - w;  // exclusive prefix of warp totals
   }
   __syncthreads();
-  const int excl = warp_tot[warp] + incl - (h0 + h1);
-  if (rank >= excl && rank < excl + h0) {
-    *sel_bin = 2 * t;
-    *sel_before = excl;
-  } else if (rank >= excl + h0 && rank < excl + h0 + h1) {
-    *sel_bin = 2 * t + 1;
-    *sel_before = excl + h0;
+  int excl = warp_tot[warp] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < kBinsPerThread; ++k) {
+    if (rank >= excl && rank < excl + h[k]) {
+      *sel_bin = kBinsPerThread * t + k;
+      *sel_before = excl;
+    }
+    excl += h[k];
   }
   __syncthreads();
 }
@@ -98,16 +115,64 @@ __device__ __forceinline__ int digit_shift(unsigned lo, unsigned hi) {
   return bits > kDigitBits ? bits - kDigitBits : 0;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// One radix-select refinement step for both wanted order statistics, after the histograms have been filled.
+__device__ void refine(SelState* st, const SelState& s0, const SelState& s1, bool need0, bool need1, bool same, int sh0, int sh1,
+                       int (*hist)[kBins], int* warp_tot, int* sel_bin, int* sel_before) {
+  const int t = threadIdx.x;
+  if (need0) {
+    find_bin(hist[0], s0.rank, warp_tot, sel_bin, sel_before);
+    if (t == 0) {
+      unsigned nlo = s0.lo + ((unsigned)*sel_bin << sh0);
+      unsigned width = (sh0 >= 32) ? 0xffffffffu : ((1u << sh0) - 1u);
+      unsigned nhi = nlo + width;
+      if (nhi > s0.hi || nhi < nlo) nhi = s0.hi;
+      st[0] = SelState{nlo, nhi, s0.rank - *sel_before};
+    }
+    __syncthreads();
+  }
+  if (need1) {
+    const int* h = same ? hist[0] : hist[1];
+    const int sh = same ? sh0 : sh1;
+    find_bin(h, s1.rank, warp_tot, sel_bin, sel_before);
+    if (t == 0) {
+      unsigned nlo = s1.lo + ((unsigned)*sel_bin << sh);
+      unsigned width = (1u << sh) - 1u;
+      unsigned nhi = nlo + width;
+      if (nhi > s1.hi || nhi < nlo) nhi = s1.hi;
+      st[1] = SelState{nlo, nhi, s1.rank - *sel_before};
+    }
+    __syncthreads();
+  }
+}
+
+// Adds one key to the selection histograms.  Keys equal to the range start are counted by ballot (zero padding would
+// otherwise serialise hundreds of thousands of same-address shared atomics); must be called by whole warps.
+__device__ __forceinline__ void hist_add(unsigned key, bool valid, const SelState& s0, const SelState& s1, bool need0, bool need1,
+                                         bool same, int sh0, int sh1, int (*hist)[kBins], int& lo0_hits) {
+  if (need0) {
+    const bool at_lo = valid && (key == s0.lo);
+    lo0_hits += __popc(__ballot_sync(0xffffffffu, at_lo));
+    if (valid && !at_lo && key > s0.lo && key <= s0.hi) atomicAdd(&hist[0][(key - s0.lo) >> sh0], 1);
+  }
+  if (need1 && !same) {
+    if (valid && key >= s1.lo && key <= s1.hi) atomicAdd(&hist[1][(key - s1.lo) >> sh1], 1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
 tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ depth, TileGrid grid, int tile_base,
                       int T, int TL, int scale, fsr_tile_params p, float* __restrict__ dem_norm,
-                      float* __restrict__ depth_norm, float* __restrict__ stats, unsigned* __restrict__ flags_out) {
+                      float* __restrict__ depth_norm, float* __restrict__ stats, float* __restrict__ dem_lr,
+                      unsigned* __restrict__ flags_out) {
+  extern __shared__ unsigned s_keys[];   // [kCap] compacted upper-tail keys
   __shared__ int hist[2][kBins];
   __shared__ int warp_tot[32];
   __shared__ float red_min[32], red_max[32];
+  __shared__ float pool_part[4][128];
   __shared__ SelState st[2];
   __shared__ int sel_bin, sel_before;
   __shared__ unsigned s_flags;
+  __shared__ int s_count;
 
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
@@ -115,8 +180,12 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   const int2 org = grid.origins[tile_base + tile_local];
   const int vec_per_row = T / 4;
   const int n_vec = T * vec_per_row;
+  const int n_px = T * T;
   unsigned my_flags = 0;
-  if (t == 0) s_flags = 0;
+  if (t == 0) {
+    s_flags = 0;
+    s_count = 0;
+  }
 
   // ---- depth_lr: nodata -> 0, finite check, log1p scaling (preprocessing.py:141-151) ----------------
   for (int i = t; i < TL * TL; i += kThreads) {
@@ -136,16 +205,114 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
     depth_norm[(size_t)tile_local * TL * TL + i] = fminf(fmaxf(s, 0.0f), 1.0f);
   }
 
-  // ---- pass A: min / max of clip(x, 0, inf) ----------------------------------------------------------
-  float vmin = INFINITY, vmax = 0.0f;
   const bool own_stats = !p.has_ref_stats;
-  for (int i = t; i < n_vec; i += kThreads) {
-    int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-    float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
-    float a = fmaxf(fix_dem(v.x, p, my_flags), 0.0f), b = fmaxf(fix_dem(v.y, p, my_flags), 0.0f);
-    float cc = fmaxf(fix_dem(v.z, p, my_flags), 0.0f), d = fmaxf(fix_dem(v.w, p, my_flags), 0.0f);
-    vmin = fminf(vmin, fminf(fminf(a, b), fminf(cc, d)));
-    vmax = fmaxf(vmax, fmaxf(fmaxf(a, b), fmaxf(cc, d)));
+  // Upper-tail fast path (default dem_pct_clip = 95): the two order statistics lie among the n_top largest keys.  A
+  // threshold estimated from a 1/8 sample lets ONE full pass compact every key >= threshold into shared memory
+  // (exact count checked afterwards), where the exact radix select runs without touching the tile again.
+  const int n_top = n_px - p.rank_lo;
+  const bool try_fast = own_stats && (long long)n_top * 14 / 10 + 2048 <= kCap && T % (4 * kSampleStep) == 0;
+  unsigned thr_key = 0;
+  if (try_fast) {
+    // sample min / max
+    float smin = INFINITY, smax = 0.0f;
+    unsigned dummy = 0;
+    for (int i = t * kSampleStep; i < n_vec; i += kThreads * kSampleStep) {
+      int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
+      float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+      float a = fmaxf(fix_dem(v.x, p, dummy), 0.0f), b = fmaxf(fix_dem(v.y, p, dummy), 0.0f);
+      float cc = fmaxf(fix_dem(v.z, p, dummy), 0.0f), d = fmaxf(fix_dem(v.w, p, dummy), 0.0f);
+      smin = fminf(smin, fminf(fminf(a, b), fminf(cc, d)));
+      smax = fmaxf(smax, fmaxf(fmaxf(a, b), fmaxf(cc, d)));
+    }
+    smin = warp_min(smin);
+    smax = warp_max(smax);
+    if (lane == 0) {
+      red_min[warp] = smin;
+      red_max[warp] = smax;
+    }
+    for (int i = t; i < kBins; i += kThreads) hist[0][i] = 0;
+    __syncthreads();
+    smin = red_min[0];
+    smax = red_max[0];
+    for (int w = 1; w < kWarps; ++w) {
+      smin = fminf(smin, red_min[w]);
+      smax = fmaxf(smax, red_max[w]);
+    }
+    const unsigned klo = __float_as_uint(smin + 0.0f), khi = __float_as_uint(smax + 0.0f);
+    if (khi > klo) {
+      const int sh = digit_shift(klo, khi);
+      for (int i = t * kSampleStep; i < n_vec; i += kThreads * kSampleStep) {
+        int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
+        float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+        float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&hist[0][(dem_key(e[j], p, dummy) - klo) >> sh], 1);
+      }
+      __syncthreads();
+      // rank (from below) of the sample element above which ~1.3 x n_top / 8 samples lie
+      const int n_samp = n_px / kSampleStep;
+      const int want_above = (int)(((long long)n_top * 13 / 10 + 512) / kSampleStep);
+      const int srank = n_samp - 1 - want_above;
+      if (srank > 0) {
+        find_bin(hist[0], srank, warp_tot, &sel_bin, &sel_before);
+        thr_key = klo + ((unsigned)sel_bin << sh);  // lower edge of that sample bin
+      }
+    }
+    __syncthreads();  // hist / red arrays are reused below
+  }
+
+  // ---- pass A: min / max of clip(x, 0, inf), finite checks, compaction of the upper tail ------------
+  float vmin = INFINITY, vmax = 0.0f;
+  const bool compact = try_fast && thr_key > 0;
+  // kUnroll independent 16-byte loads per thread are issued before any is consumed: the pass is HBM-latency bound
+  for (int i0 = t; i0 < n_vec; i0 += kThreads * kUnroll) {
+    float4 vv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = i0 + u * kThreads;
+      int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
+      vv[u] = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+    const float4 v = vv[u];
+    float e[4];
+    e[0] = fmaxf(fix_dem(v.x, p, my_flags), 0.0f);
+    e[1] = fmaxf(fix_dem(v.y, p, my_flags), 0.0f);
+    e[2] = fmaxf(fix_dem(v.z, p, my_flags), 0.0f);
+    e[3] = fmaxf(fix_dem(v.w, p, my_flags), 0.0f);
+    vmin = fminf(vmin, fminf(fminf(e[0], e[1]), fminf(e[2], e[3])));
+    vmax = fmaxf(vmax, fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])));
+    if (compact) {
+      unsigned k[4];
+      int mine = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        k[j] = __float_as_uint(e[j] + 0.0f);
+        mine += k[j] >= thr_key ? 1 : 0;
+      }
+      // warp-aggregated append: one shared atomic per warp per iteration
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int base = 0;
+      if (total > 0) {
+        if (lane == 31) base = atomicAdd(&s_count, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k[j] >= thr_key) {
+            if (pos < kCap) s_keys[pos] = k[j];
+            ++pos;
+          }
+      }
+    }
+  }
   }
   vmin = warp_min(vmin);
   vmax = warp_max(vmax);
@@ -156,11 +323,10 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   if (my_flags) atomicOr(&s_flags, my_flags);
   __syncthreads();
   if (warp == 0) {
-    float a = warp_min(red_min[lane]), b = warp_max(red_max[lane]);
+    float a = warp_min(lane < kWarps ? red_min[lane] : INFINITY), b = warp_max(lane < kWarps ? red_max[lane] : 0.0f);
     if (lane == 0) {
       red_min[0] = a;
       red_max[0] = b;
-      // +0.0f canonicalises -0.0 so that keys are the plain bit patterns of non-negative floats
       st[0] = SelState{__float_as_uint(a + 0.0f), __float_as_uint(b + 0.0f), p.rank_lo};
       st[1] = SelState{__float_as_uint(a + 0.0f), __float_as_uint(b + 0.0f), p.rank_hi};
     }
@@ -168,8 +334,18 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   __syncthreads();
   vmin = red_min[0];
   vmax = red_max[0];
+  // the compacted set is usable when it holds every key of rank >= rank_lo and did not overflow
+  const int n_comp = s_count;
+  const bool fast = compact && n_comp <= kCap && n_comp >= n_top;
+  if (fast && t == 0) {
+    const int below = n_px - n_comp;  // keys smaller than the threshold
+    st[0] = SelState{thr_key, __float_as_uint(vmax + 0.0f), p.rank_lo - below};
+    st[1] = SelState{thr_key, __float_as_uint(vmax + 0.0f), p.rank_hi - below};
+  }
+  __syncthreads();
 
   // ---- passes B..: radix select of sorted[rank_lo] and sorted[rank_hi] ------------------------------
+  // range-adaptive 11-bit digits; over the compacted keys in shared memory (fast path) or over the tile in L2
   for (int guard = 0; own_stats && guard < 8; ++guard) {
     const SelState s0 = st[0], s1 = st[1];
     const bool need0 = s0.hi > s0.lo, need1 = s1.hi > s1.lo;
@@ -179,52 +355,26 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
     const int sh1 = need1 ? digit_shift(s1.lo, s1.hi) : 0;
     for (int i = t; i < 2 * kBins; i += kThreads) (&hist[0][0])[i] = 0;
     __syncthreads();
-    int lo0_hits = 0;  // keys equal to the range start are counted by ballot: zero padding would otherwise
-                       // serialise hundreds of thousands of same-address shared atomics
-    for (int i = t; i < n_vec; i += kThreads) {
-      int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-      float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
-      unsigned dummy = 0;
-      float e[4] = {v.x, v.y, v.z, v.w};
+    int lo0_hits = 0;
+    if (fast) {
+      const int n_round = (n_comp + 31) & ~31;
+      for (int i = t; i < n_round; i += kThreads) {
+        const bool valid = i < n_comp;
+        hist_add(valid ? s_keys[i] : 0u, valid, s0, s1, need0, need1, same, sh0, sh1, hist, lo0_hits);
+      }
+    } else {
+      for (int i = t; i < n_vec; i += kThreads) {
+        int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
+        float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+        unsigned dummy = 0;
+        float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        unsigned key = __float_as_uint(fmaxf(fix_dem(e[j], p, dummy), 0.0f) + 0.0f);
-        if (need0) {
-          bool at_lo = (key == s0.lo);
-          lo0_hits += __popc(__ballot_sync(0xffffffffu, at_lo));
-          if (!at_lo && key > s0.lo && key <= s0.hi) atomicAdd(&hist[0][(key - s0.lo) >> sh0], 1);
-        }
-        if (need1 && !same) {
-          if (key >= s1.lo && key <= s1.hi) atomicAdd(&hist[1][(key - s1.lo) >> sh1], 1);
-        }
+        for (int j = 0; j < 4; ++j) hist_add(dem_key(e[j], p, dummy), true, s0, s1, need0, need1, same, sh0, sh1, hist, lo0_hits);
       }
     }
     if (need0 && lane == 0 && lo0_hits) atomicAdd(&hist[0][0], lo0_hits);
     __syncthreads();
-    if (need0) {
-      find_bin(hist[0], s0.rank, warp_tot, &sel_bin, &sel_before);
-      if (t == 0) {
-        unsigned nlo = s0.lo + ((unsigned)sel_bin << sh0);
-        unsigned width = (sh0 >= 32) ? 0xffffffffu : ((1u << sh0) - 1u);
-        unsigned nhi = nlo + width;
-        if (nhi > s0.hi || nhi < nlo) nhi = s0.hi;
-        st[0] = SelState{nlo, nhi, s0.rank - sel_before};
-      }
-      __syncthreads();
-    }
-    if (need1) {
-      const int* h = same ? hist[0] : hist[1];
-      const int sh = same ? sh0 : sh1;
-      find_bin(h, s1.rank, warp_tot, &sel_bin, &sel_before);
-      if (t == 0) {
-        unsigned nlo = s1.lo + ((unsigned)sel_bin << sh);
-        unsigned width = (1u << sh) - 1u;
-        unsigned nhi = nlo + width;
-        if (nhi > s1.hi || nhi < nlo) nhi = s1.hi;
-        st[1] = SelState{nlo, nhi, s1.rank - sel_before};
-      }
-      __syncthreads();
-    }
+    refine(st, s0, s1, need0, need1, same, sh0, sh1, hist, warp_tot, &sel_bin, &sel_before);
   }
 
   // ---- numpy _lerp on the two order statistics (float32, no FMA contraction) -------------------------
@@ -254,19 +404,44 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   }
 
   // ---- pass N: clip to [0, p_clip], min-max scale, clip to [0, 1] (preprocessing.py:91-94) -----------
+  // plus, when dem_lr != nullptr, the scale x scale average pooling of the normalised tile that feeds the network's
+  // low-resolution branch (the graph's AveragePool on dem_hr): fixed summation order, no atomics.
   float4* out = reinterpret_cast<float4*>(dem_norm + (size_t)tile_local * T * T);
-  for (int i = t; i < n_vec; i += kThreads) {
-    int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-    float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
-    unsigned dummy = 0;
-    float e[4] = {v.x, v.y, v.z, v.w};
+  const bool pool = dem_lr != nullptr && scale == 16 && T == 512 && kUnroll == 4;  // thread <-> (row offset t / 128, column vector t % 128)
+  for (int i0 = t; i0 < n_vec; i0 += kThreads * kUnroll) {
+    float4 vv[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x = fminf(fmaxf(fix_dem(e[j], p, dummy), 0.0f), p_clip);
-      float n = __fdiv_rn(__fsub_rn(x, dem_min), range_f);
-      e[j] = zero_out ? 0.0f : fminf(fmaxf(n, 0.0f), 1.0f);
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = i0 + u * kThreads;
+      int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
+      vv[u] = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
     }
-    out[i] = make_float4(e[0], e[1], e[2], e[3]);
+    float psum = 0.0f;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      unsigned dummy = 0;
+      float e[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = fminf(fmaxf(fix_dem(e[j], p, dummy), 0.0f), p_clip);
+        float n = __fdiv_rn(__fsub_rn(x, dem_min), range_f);
+        e[j] = zero_out ? 0.0f : fminf(fmaxf(n, 0.0f), 1.0f);
+      }
+      out[i0 + u * kThreads] = make_float4(e[0], e[1], e[2], e[3]);
+      psum += (e[0] + e[1]) + (e[2] + e[3]);
+    }
+    if (pool) {
+      // one outer iteration = kUnroll x 4 = 16 tile rows = one row of pooled cells
+      float q = psum + __shfl_xor_sync(0xffffffffu, psum, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      if ((lane & 3) == 0) pool_part[t >> 7][(t & 127) >> 2] = q;   // [row offset][cell]
+      __syncthreads();
+      if (t < 32) {
+        const float sum = (pool_part[0][t] + pool_part[1][t]) + (pool_part[2][t] + pool_part[3][t]);
+        dem_lr[(size_t)tile_local * (TL * TL) + (i0 / (kThreads * kUnroll)) * TL + t] = sum * (1.0f / 256.0f);
+      }
+      __syncthreads();
+    }
   }
   __syncthreads();
   if (t == 0 && s_flags) atomicOr(flags_out, s_flags);
@@ -302,12 +477,17 @@ __global__ void tile_passthrough_kernel(const float* __restrict__ dem, const flo
 
 void launch_tile_normalize(const float* d_dem, const float* d_depth, const TileGrid& grid, int tile_base, int n_tiles,
                            int T, int TL, int scale, const fsr_tile_params& p, float* d_dem_norm, float* d_depth_norm,
-                           float* d_stats, unsigned* d_flags, cudaStream_t stream) {
+                           float* d_stats, float* d_dem_lr, unsigned* d_flags, cudaStream_t stream) {
   if (n_tiles <= 0) return;
   FSR_REQUIRE(T % 4 == 0 && T * (T / 4) % kThreads == 0, "hr tile must be a multiple of 64 pixels");
   if (p.normalize_inputs) {
-    tile_normalize_kernel<<<n_tiles, kThreads, 0, stream>>>(d_dem, d_depth, grid, tile_base, T, TL, scale, p, d_dem_norm,
-                                                            d_depth_norm, d_stats, d_flags);
+    static bool attr = false;
+    if (!attr) {
+      FSR_CUDA(cudaFuncSetAttribute(tile_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * (int)sizeof(unsigned)));
+      attr = true;
+    }
+    tile_normalize_kernel<<<n_tiles, kThreads, kCap * sizeof(unsigned), stream>>>(d_dem, d_depth, grid, tile_base, T, TL, scale, p,
+                                                                                 d_dem_norm, d_depth_norm, d_stats, d_dem_lr, d_flags);
   } else {
     tile_passthrough_kernel<<<n_tiles, 1024, 0, stream>>>(d_dem, d_depth, grid, tile_base, T, TL, scale, d_dem_norm,
                                                           d_depth_norm, d_flags);
