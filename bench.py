@@ -32,6 +32,8 @@ import numpy as np
 REPO = Path(__file__).resolve().parent
 if str(REPO) not in sys.path:
     sys.path.insert(0, str(REPO))
+# stdout carries exactly one JSON line: keep NCCL's own banner / debug output on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "hires_mpx_per_s"
 UNIT = "Mpx/s"
@@ -43,7 +45,7 @@ OVERLAP_LR = 8
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FLOODSR_B200_PRECISION", "fp16"), choices=["fp32", "bf16", "fp16"])
@@ -68,7 +70,7 @@ def find_model(tmpdir: Path) -> tuple[Path, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -80,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device_index)],
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.device_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             threading.Thread(target=self._pump, daemon=True).start()
@@ -132,7 +134,7 @@ def head_traffic_per_launch(flops_per_launch: float):
         return None
 
 
-def cpu_reference_rate(model_fp: Path, sample_hw=(1024, 1536), steps: int = 1, warmup: int = 0) -> dict:
+def cpu_reference_rate(model_fp: Path, sample_hw=(2048, 3072), steps: int = 1, warmup: int = 0) -> dict:
     """Oracle (CPU restatement of the reference path) on a bounded sample raster: hires Mpx/s."""
     import torch
 
@@ -308,6 +310,23 @@ def main():
     mpx = H * W / 1e6
     value = mpx / (ms_per_step / 1e3)
 
+    # ---- head kernel alone (no convT running beside it): explains the in-step roofline figure ------------
+    head_isolated = None
+    if args.precision != "fp32":
+        os.environ["FSR_HR_OVERLAP"] = "0"
+        eng_iso = EngineB200(model_fp, precision=args.precision, device=local_rank)
+        del os.environ["FSR_HR_OVERLAP"]
+        ex_iso = CudaBandExecutor(eng_iso, H, W, "feather", overlap_hr)
+        for _ in range(2):
+            run_band_step(ex_iso, plan, plans, d_depth, d_dem, r0, None, None, d_out)
+        torch.cuda.synchronize()
+        eng_iso.profile(True)
+        run_band_step(ex_iso, plan, plans, d_depth, d_dem, r0, None, None, d_out)
+        torch.cuda.synchronize()
+        head_isolated = eng_iso.profile_fetch()["head"]
+        eng_iso.close()
+        del ex_iso, eng_iso
+
     # ---- end-to-end leg ---------------------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -358,7 +377,13 @@ def main():
         "ms_per_launch": head_ms / max(head_launches, 1),
         "launches": head_launches,
         "traffic": head_traffic_per_launch(head_flops / max(head_launches, 1)),
+        "note": "timed inside the step, where the persistent head grid is capped at 96 SMs and the HBM-write-bound transposed "
+                "convolution of the next sub-chunk runs beside it; 'isolated' = same kernel alone on all SMs",
     }
+    if head_isolated is not None and head_isolated[0] > 0:
+        iso_tf = 2.0 * head_macs_tile * n_tiles_mine / (head_isolated[0] / 1e3) / 1e12
+        roofline["isolated"] = {"achieved": iso_tf, "frac": iso_tf / peak_tf, "ms_per_launch": head_isolated[0] / max(head_isolated[1], 1),
+                                "launches": head_isolated[1]}
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
     hbm_gbs = float(peaks.get("hbm_gbs", 6650.0))
     # memory-bound stages: algorithmic bytes per step on this rank
@@ -372,7 +397,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_reference_rate(model_fp)
+        cb = cpu_reference_rate(model_fp, steps=2, warmup=1)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
@@ -395,6 +420,7 @@ def main():
             "tiles_per_step": n_tiles_total,
             "gflop_per_tile": 2 * eng.macs_per_tile() / 1e9,
             "l2_policy": "inputs larger than L2 (512 MiB DEM band per GPU vs 126 MB L2), no explicit flush",
+            "precision": f"{args.precision} operands, fp32 accumulate (tcgen05 kind::f16)" if args.precision != "fp32" else "fp32 CUDA-core FMA",
             "parallelism": f"row-bands x{world}",
         },
         "roofline": roofline,

@@ -90,9 +90,12 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
     if (prop.major != 10) throw Error(FSR_E_UNSUPPORTED, "the tensor-core backends need an sm_100 (Blackwell) device: tcgen05/TMEM/TMA");
     n_sms_ = prop.multiProcessorCount;
     chunk_tiles_ = 1024;  // the batched low-resolution layers need many tiles per launch to fill 148 SMs
-    hr_sub_ = 32;  // the HR feature map of a sub-chunk streams through HBM; long head launches amortise their prologue
+    hr_sub_ = 64;  // the HR feature map of a sub-chunk streams through HBM; long head launches amortise their prologue
     if (const char* e = getenv("FSR_HR_SUB")) hr_sub_ = std::max(1, atoi(e));
     if (const char* e = getenv("FSR_CHUNK")) chunk_tiles_ = std::max(1, atoi(e));
+    if (const char* e = getenv("FSR_HR_OVERLAP")) hr_overlap_ = atoi(e) != 0;
+    head_sms_ = std::min(n_sms_, 96);  // measured best split on a 148-SM B200: 96 SMs head, the rest free for convT
+    if (const char* e = getenv("FSR_HEAD_SMS")) head_sms_ = std::max(1, std::min(n_sms_, atoi(e)));
     tc_prepare(weights);
   }
 }
@@ -104,6 +107,10 @@ Engine::~Engine() {
                        &d_in_depth, &d_in_dem, &d_out, &d_tmp_a, &d_tmp_b})
     b->release();
   win.release();
+  d_big2_.release();
+  if (s_hd_) cudaStreamDestroy(s_hd_);
+  if (s_ct_) cudaStreamDestroy(s_ct_);
+  for (auto e : ev_ring_) if (e) cudaEventDestroy(e);
   d_halo[0].release();
   d_halo[1].release();
   if (s_comp) cudaStreamDestroy(s_comp);
@@ -231,7 +238,7 @@ void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_
     if (precision_ != FSR_PREC_FP32) {
       tbase_[hdr_.out_tensor] = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
       tc_run_ops(false, n, 0, nullptr, max_depth, denom, s);
-      for (int sub = 0; sub < n; sub += hr_sub_) tc_run_ops(true, std::min(hr_sub_, n - sub), sub, pm, max_depth, denom, s);
+      tc_run_hr_phase(n, pm, max_depth, denom, s);
       continue;
     }
     // fp32 path always materialises the normalised prediction, then inverts it

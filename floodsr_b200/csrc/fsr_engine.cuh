@@ -153,6 +153,14 @@ class Engine {
   void tc_ensure_arena(int cap);
   long long tc_plane(int tid) const;
   void tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  void tc_run_one(int op, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int head_sms);
+  void tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  // convT / head overlap across sub-chunks (tc_run_hr_phase)
+  bool hr_overlap_ = true;
+  int head_sms_ = 96;
+  cudaStream_t s_hd_ = nullptr, s_ct_ = nullptr;
+  cudaEvent_t ev_ring_[9] = {};
+  DeviceBuf d_big2_;
   std::vector<char> tc_fmt_;     // 1: CP8 bf16, 0: NHWC fp32
   std::vector<int> tc_cpad_;     // channels as stored
   std::vector<TcOp> tc_ops_;
@@ -164,7 +172,7 @@ class Engine {
   std::vector<char> op_hr_;      // op touches a big tensor
   int device_ = 0, precision_ = 0, n_sms_ = 148;
   int cap_tiles_ = 0;            // arena capacity (tiles per chunk)
-  int hr_sub_ = 4;               // tiles per HR sub-chunk (tensor-core modes: 32; env FSR_HR_SUB overrides)
+  int hr_sub_ = 4;               // tiles per HR sub-chunk (tensor-core modes: 64; env FSR_HR_SUB overrides)
   int chunk_tiles_ = 64;
   int band_tiles_ = 192;         // windows per band of the fsr_run_raster copy/compute pipeline (env FSR_BAND_TILES)
   DeviceBuf d_weights_, d_flags_, d_headmid_;

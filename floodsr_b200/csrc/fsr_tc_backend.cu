@@ -220,6 +220,56 @@ long long Engine::tc_plane(int tid) const {
 }
 
 void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    if ((op_hr_[i] != 0) != hr_phase || (int)i == skip_op_) continue;
+    tc_run_one((int)i, n, sub_start, d_pred_m, max_depth, denom, s, n_sms_);
+  }
+}
+
+// High-resolution phase of one chunk.  When it is the usual pair (transposed convolution -> fused head) the two kernels of
+// consecutive sub-chunks overlap: the convT of sub-chunk k+1 (HBM-write bound) runs on its own stream next to the head of
+// sub-chunk k (tensor / shared-memory bound), the head's persistent grid being capped so that some SMs are left for it.
+// The feature map is double-buffered; events order producer and consumer.
+void Engine::tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
+  std::vector<int> hr_ops;
+  for (size_t i = 0; i < ops_.size(); ++i)
+    if (op_hr_[i] && (int)i != skip_op_) hr_ops.push_back((int)i);
+  const bool pair = hr_ops.size() == 2 && ops_[hr_ops[0]].kind == FSR_OP_CONVT && ops_[hr_ops[1]].kind == FSR_OP_HEAD &&
+                    ops_[hr_ops[1]].src0 == ops_[hr_ops[0]].dst;
+  if (!hr_overlap_ || !pair || n <= hr_sub_) {
+    for (int sub = 0; sub < n; sub += hr_sub_) tc_run_ops(true, std::min(hr_sub_, n - sub), sub, d_pred_m, max_depth, denom, s);
+    return;
+  }
+  const int ct = hr_ops[0], hd = hr_ops[1], ftid = ops_[ct].dst;
+  if (!s_hd_) {
+    int lo = 0, hi = 0;
+    FSR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = greatest priority (numerically lowest)
+    FSR_CUDA(cudaStreamCreateWithPriority(&s_hd_, cudaStreamNonBlocking, hi));
+    FSR_CUDA(cudaStreamCreateWithPriority(&s_ct_, cudaStreamNonBlocking, lo));
+    for (auto& e : ev_ring_) FSR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  d_big2_.ensure(tbuf_[ftid].bytes);
+  float* bufs[2] = {tbuf_[ftid].as<float>(), d_big2_.as<float>()};
+  cudaEvent_t ev_start = ev_ring_[8];
+  FSR_CUDA(cudaEventRecord(ev_start, s));
+  FSR_CUDA(cudaStreamWaitEvent(s_ct_, ev_start, 0));
+  FSR_CUDA(cudaStreamWaitEvent(s_hd_, ev_start, 0));
+  int k = 0;
+  for (int sub = 0; sub < n; sub += hr_sub_, ++k) {
+    const int m = std::min(hr_sub_, n - sub);
+    tbase_[ftid] = bufs[k & 1];
+    if (k >= 2) FSR_CUDA(cudaStreamWaitEvent(s_ct_, ev_ring_[4 + ((k - 2) & 3)], 0));  // the head that read this buffer is done
+    tc_run_one(ct, m, sub, d_pred_m, max_depth, denom, s_ct_, n_sms_);
+    FSR_CUDA(cudaEventRecord(ev_ring_[k & 3], s_ct_));
+    FSR_CUDA(cudaStreamWaitEvent(s_hd_, ev_ring_[k & 3], 0));
+    tc_run_one(hd, m, sub, d_pred_m, max_depth, denom, s_hd_, head_sms_);
+    FSR_CUDA(cudaEventRecord(ev_ring_[4 + (k & 3)], s_hd_));
+  }
+  FSR_CUDA(cudaStreamWaitEvent(s, ev_ring_[4 + ((k - 1) & 3)], 0));
+  tbase_[ftid] = bufs[0];
+}
+
+void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int head_sms) {
   const float* W = d_weights_.as<float>();
   const int half = precision_ == FSR_PREC_FP16 ? 1 : 0;
   auto wp = [&](int off) -> const float* { return off >= 0 ? W + off : nullptr; };
@@ -236,8 +286,7 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
     const auto& t = tensors_[tid];
     return tbase_[tid] + (size_t)sub_start * t.h * t.w * t.c;
   };
-  for (size_t i = 0; i < ops_.size(); ++i) {
-    if ((op_hr_[i] != 0) != hr_phase || (int)i == skip_op_) continue;
+  {
     const fsr_op& op = ops_[i];
     TcOp& tc = tc_ops_[i];
     const auto& ts = tensors_[op.src0];
@@ -305,7 +354,7 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
           pm = d_tmp_b.as<float>();
         }
         launch_head2_tc(cp8(op.src0), tc_plane(op.src0), tc.wpack.as<__nv_bfloat16>(), tc.h_w2.data(), &tc.h_b2, f32(op.src1), pm, pn,
-                        n, td.h, td.w, ts.c, op.cout, op.k, op.act, op.alpha, max_depth, denom, half, n_sms_, s);
+                        n, td.h, td.w, ts.c, op.cout, op.k, op.act, op.alpha, max_depth, denom, half, head_sms, s);
         break;
       }
       default:
