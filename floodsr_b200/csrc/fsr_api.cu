@@ -579,10 +579,19 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   e.d_in_dem.ensure((size_t)H * W * sizeof(float));
   e.d_out.ensure((size_t)H * W * sizeof(float));
   e.d_stats.ensure((size_t)ny * nx * 3 * sizeof(float));
-  // band size: enough windows per band to keep the batched layer kernels efficient, small enough to overlap copies
+  // band plan: enough windows per band to keep the batched layer kernels efficient, small enough to overlap copies;
+  // the first and the last band are a single window row, so the pipeline fills (first H2D) and drains (last D2H) fast
   int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
-  if (ny <= rows_per_band) rows_per_band = ny;
-  const int n_bands = ceil_div(ny, rows_per_band);
+  std::vector<int> band_ty;  // band b covers window rows [band_ty[b], band_ty[b + 1])
+  band_ty.push_back(0);
+  if (ny >= 3 && rows_per_band > 1) {
+    band_ty.push_back(1);
+    while (band_ty.back() < ny - 1) band_ty.push_back(std::min(band_ty.back() + rows_per_band, (int)ny - 1));
+  } else {
+    while (band_ty.back() + rows_per_band < ny) band_ty.push_back(band_ty.back() + rows_per_band);
+  }
+  band_ty.push_back(ny);
+  const int n_bands = (int)band_ty.size() - 1;
   e.d_halo[0].ensure((size_t)T * W * sizeof(float));
   e.d_halo[1].ensure((size_t)T * W * sizeof(float));
   std::vector<cudaEvent_t> ev_in(n_bands), ev_done(n_bands);
@@ -601,7 +610,7 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, (size_t)Hl * Wl * sizeof(float), cudaMemcpyHostToDevice, si));
   int copied = 0;
   for (int b = 0; b < n_bands; ++b) {
-    const int ty1 = std::min((b + 1) * rows_per_band, (int)ny);
+    const int ty1 = band_ty[b + 1];
     const int need = b == n_bands - 1 ? H : std::min(e.win.ys[ty1 - 1] + T, (int)H);
     if (need > copied) {
       FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.as<float>() + (size_t)copied * W, dem_hr + (size_t)copied * W,
@@ -611,7 +620,7 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
     FSR_CUDA(cudaEventRecord(ev_in[b], si));
   }
   for (int b = 0; b < n_bands; ++b) {
-    const int ty0 = b * rows_per_band, ty1 = std::min(ty0 + rows_per_band, (int)ny);
+    const int ty0 = band_ty[b], ty1 = band_ty[b + 1];
     FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[b], 0));
     band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), 0, H, ty0, ty1, *params, e.d_halo[b & 1].as<float>(),
              e.d_stats.as<float>() + (size_t)ty0 * nx * 3, sc_);
