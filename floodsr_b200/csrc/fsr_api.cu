@@ -108,6 +108,8 @@ Engine::~Engine() {
     b->release();
   win.release();
   d_big2_.release();
+  fused_hw_.release();
+  fused_wt_.release();
   if (s_hd_) cudaStreamDestroy(s_hd_);
   if (s_ct_) cudaStreamDestroy(s_ct_);
   for (auto e : ev_ring_) if (e) cudaEventDestroy(e);

@@ -155,6 +155,11 @@ class Engine {
   void tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
   void tc_run_one(int op, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int head_sms);
   void tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  void tc_prepare_fused(const float* host_weights);
+  void tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  int fused_ct_ = -1, fused_hd_ = -1;   // plan ops run by the fused high-resolution kernel, or -1
+  DeviceBuf fused_hw_, fused_wt_;
+  std::vector<float> fused_bias_t_;
   // convT / head overlap across sub-chunks (tc_run_hr_phase)
   bool hr_overlap_ = true;
   int head_sms_ = 96;

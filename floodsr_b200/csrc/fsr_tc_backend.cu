@@ -39,6 +39,16 @@ void launch_head2_tc(const __nv_bfloat16* feat, long long plane, const __nv_bflo
                      const float* dem, float* pred_m, float* pred_norm, int n_img, int H, int W, int cin, int cmid, int ksz,
                      int act, float alpha, float max_depth, float denom, int half, int n_sms, cudaStream_t s);
 
+bool fused_hr_ok(int H, int W, int lr_h, int lr_w, int cin_t, int cout_t, int k_t, int cmid, int ksz);
+size_t fused_hw_elems();
+size_t fused_wt_elems();
+void fused_pack_head(const float* w, const float* bias, uint16_t* dst, uint16_t (*cvt)(float), float (*back)(uint16_t));
+void fused_pack_convt(const float* w, uint16_t* dst, uint16_t (*cvt)(float));
+void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfloat16* wt_pack, const float* bias_t, int act_t,
+                        float alpha_t, const __nv_bfloat16* hw_pack, const float* w2, const float* b2, int act_h, float alpha_h,
+                        const float* dem, float* pred_m, float* pred_norm, int n_img, int H, float max_depth, float denom,
+                        int half, int n_sms, cudaStream_t s);
+
 static bool g_pack_half = false;  // 16-bit format used while packing weights (set by tc_prepare)
 static inline uint16_t f2bf(float f) {
   uint16_t u;
@@ -196,11 +206,60 @@ void Engine::tc_prepare(const float* w) {
       need_cp8(op.dst, "layer output");
     }
   }
+  tc_prepare_fused(w);
+}
+
+// The usual high-resolution tail (16x transposed convolution -> fused head) runs as ONE kernel that never writes the
+// feature map to HBM (k_tc_fused.cu); anything else falls back to the convT + head kernel pair.
+void Engine::tc_prepare_fused(const float* w) {
+  fused_ct_ = fused_hd_ = -1;
+  if (getenv("FSR_NO_FUSED_HR")) return;
+  std::vector<int> hr_ops;
+  for (size_t i = 0; i < ops_.size(); ++i)
+    if (op_hr_[i]) hr_ops.push_back((int)i);
+  if (hr_ops.size() != 2) return;
+  const fsr_op& ct = ops_[hr_ops[0]];
+  const fsr_op& hd = ops_[hr_ops[1]];
+  if (ct.kind != FSR_OP_CONVT || hd.kind != FSR_OP_HEAD || hd.src0 != ct.dst || hd.src1 != 1) return;
+  const auto& tl = tensors_[ct.src0];
+  const auto& tf = tensors_[ct.dst];
+  if (!tc_fmt_[ct.src0] || tc_cpad_[ct.src0] != 32) return;
+  if (!fused_hr_ok(tf.h, tf.w, tl.h, tl.w, tl.c, ct.cout, ct.k, hd.cout, hd.k)) return;
+  std::vector<uint16_t> hw(fused_hw_elems(), 0), wt(fused_wt_elems(), 0);
+  fused_pack_head(w + hd.w_off, hd.b_off >= 0 ? w + hd.b_off : nullptr, hw.data(), f2bf, bf2f);
+  fused_pack_convt(w + ct.w_off, wt.data(), f2bf);
+  fused_hw_.ensure(hw.size() * 2);
+  fused_wt_.ensure(wt.size() * 2);
+  FSR_CUDA(cudaMemcpy(fused_hw_.p, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  FSR_CUDA(cudaMemcpy(fused_wt_.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+  fused_bias_t_.assign(ct.cout, 0.f);
+  if (ct.b_off >= 0) std::copy(w + ct.b_off, w + ct.b_off + ct.cout, fused_bias_t_.begin());
+  fused_ct_ = hr_ops[0];
+  fused_hd_ = hr_ops[1];
+}
+
+void Engine::tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
+  const fsr_op& ct = ops_[fused_ct_];
+  const fsr_op& hd = ops_[fused_hd_];
+  const TcOp& th = tc_ops_[fused_hd_];
+  const auto& tf = tensors_[ct.dst];
+  const int half = precision_ == FSR_PREC_FP16 ? 1 : 0;
+  float* pn = tbase_[hd.dst];  // may be nullptr when the caller does not want the normalised prediction
+  float* pm = d_pred_m;
+  if (!pm) {
+    d_tmp_b.ensure((size_t)n * tf.h * tf.w * sizeof(float));
+    pm = d_tmp_b.as<float>();
+  }
+  ProfScope scope(prof, PROF_HEAD, s);
+  launch_fused_hr_tc(reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]), tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(),
+                     fused_bias_t_.data(), ct.act, ct.alpha, fused_hw_.as<__nv_bfloat16>(), th.h_w2.data(), &th.h_b2, hd.act, hd.alpha,
+                     tbase_[1], pm, pn, n, tf.h, max_depth, denom, half, n_sms_, s);
 }
 
 void Engine::tc_ensure_arena(int cap) {
   for (size_t i = 0; i < tensors_.size(); ++i) {
     if ((int)i == 0 || (int)i == 1 || (int)i == hdr_.out_tensor) continue;
+    if (fused_ct_ >= 0 && (int)i == ops_[fused_ct_].dst) continue;  // the feature map stays on chip
     const auto& t = tensors_[i];
     const size_t tiles = big_[i] ? hr_sub_ : cap;
     const size_t elt = tc_fmt_[i] ? 2 : 4;
@@ -231,6 +290,10 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
 // sub-chunk k (tensor / shared-memory bound), the head's persistent grid being capped so that some SMs are left for it.
 // The feature map is double-buffered; events order producer and consumer.
 void Engine::tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
+  if (fused_ct_ >= 0 && skip_op_ != fused_ct_ && skip_op_ != fused_hd_) {
+    tc_run_fused(n, d_pred_m, max_depth, denom, s);
+    return;
+  }
   std::vector<int> hr_ops;
   for (size_t i = 0; i < ops_.size(); ++i)
     if (op_hr_[i] && (int)i != skip_op_) hr_ops.push_back((int)i);
