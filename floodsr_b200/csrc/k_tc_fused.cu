@@ -96,6 +96,8 @@ struct RowIter {  // items of this CTA's row range; every warp role iterates the
   }
 };
 
+// try_wait with a short suspend-time hint: the rings here are only 2-3 deep, so a hand-off must be seen within a fraction
+// of a row time (a 2 us hint serialised builder and head), while plain spinning would steal shared-memory bandwidth
 __device__ __forceinline__ void wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   for (;;) {
@@ -107,10 +109,10 @@ __device__ __forceinline__ void wait_relaxed(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(96u)
         : "memory");
     if (ok) return;
-    if (++spins > (1u << 22)) __trap();
+    if (++spins > (1u << 26)) __trap();
   }
 }
 
