@@ -312,7 +312,7 @@ def main():
 
     # ---- head kernel alone (no convT running beside it): explains the in-step roofline figure ------------
     head_isolated = None
-    if args.precision != "fp32":
+    if args.precision != "fp32" and os.environ.get("FSR_NO_FUSED_HR"):
         os.environ["FSR_HR_OVERLAP"] = "0"
         eng_iso = EngineB200(model_fp, precision=args.precision, device=local_rank)
         del os.environ["FSR_HR_OVERLAP"]
@@ -361,13 +361,18 @@ def main():
     hh, hw, _ = lm.tensors[head_op.dst]
     cin_head = lm.tensors[head_op.src0][2] + 1
     head_macs_tile = hh * hw * (head_op.k * head_op.k * cin_head * head_op.cout + head_op.cout)
+    fused = args.precision != "fp32" and prof["convt"][1] == 0  # the fused kernel also does the transposed convolution
+    if fused:
+        ct_op = lm.ops[-2]
+        head_macs_tile += hh * hw * lm.tensors[ct_op.src0][2] * ct_op.cout
     tiles_timed = n_tiles_mine * args.steps
     head_flops = 2.0 * head_macs_tile * tiles_timed
     achieved_tf = head_flops / (head_ms / 1e3) / 1e12 if head_ms > 0 else 0.0
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0)) if args.precision != "fp32" else float(peaks.get("bf16_tflops_sustained", 1400.0))
     roofline = {
         "bound": "tensor",
-        "kernel": "head_tc_kernel (fused conv3x3+DEM+act+conv1x1+expm1, tcgen05)" if args.precision != "fp32" else "conv_igemm_fp32_kernel (head)",
+        "kernel": ("fused_hr_kernel (convT16x16+act -> conv3x3+DEM+act -> conv1x1 -> expm1, tcgen05)" if fused else
+                   "head_tc_kernel (fused conv3x3+DEM+act+conv1x1+expm1, tcgen05)") if args.precision != "fp32" else "conv_igemm_fp32_kernel (head)",
         "achieved": achieved_tf,
         "peak": peak_tf,
         "unit": "TFLOP/s",
@@ -377,10 +382,9 @@ def main():
         "ms_per_launch": head_ms / max(head_launches, 1),
         "launches": head_launches,
         "traffic": head_traffic_per_launch(head_flops / max(head_launches, 1)),
-        "note": "timed inside the step, where the persistent head grid is capped at 96 SMs and the HBM-write-bound transposed "
-                "convolution of the next sub-chunk runs beside it; 'isolated' = same kernel alone on all SMs",
+        "note": "timed inside the step with CUDA events around each launch; FLOPs = transposed convolution + head of the tiles in the launch",
     }
-    if head_isolated is not None and head_isolated[0] > 0:
+    if not fused and head_isolated is not None and head_isolated[0] > 0:
         iso_tf = 2.0 * head_macs_tile * n_tiles_mine / (head_isolated[0] / 1e3) / 1e12
         roofline["isolated"] = {"achieved": iso_tf, "frac": iso_tf / peak_tf, "ms_per_launch": head_isolated[0] / max(head_isolated[1], 1),
                                 "launches": head_isolated[1]}

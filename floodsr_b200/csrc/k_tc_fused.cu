@@ -44,14 +44,15 @@ constexpr int kW = 512, kCells = 32, kUp = 16;
 constexpr int kRowPx = kW + 2;                    // + zero halo pixel left and right
 constexpr int kFPlane = kRowPx * 16;              // 8224 B: one 8-channel plane of an F row
 constexpr int kFRow = 4 * kFPlane;                // 32896 B
-constexpr int kFStages = 2;
+constexpr int kFStages = 3;
 constexpr int kHwBlocks = 5;                      // [ky2|ky1|ky0|ky2|ky1]
 constexpr int kHwStep = 2 * kHwBlocks * kC * 16;  // one K step of the head weights: [2 planes][160][8] = 5120 B
 constexpr int kHwBytes = 7 * kHwStep;             // 6 feature K steps + DEM/bias operand
 constexpr int kWtRow = 4 * 4 * 128 * 16;          // convT weights of one ky: [4 blocks][4 K planes][128 rows][8] = 32 KB
 constexpr int kLRow = 4 * kCells * 16;            // L cells of one LR row: [4 K planes][32 cells][8] = 2 KB
-constexpr int kWtStage = kWtRow + kLRow;
-constexpr int kWtStages = 2;
+constexpr int kWtHalf = kWtRow / 2;               // a weight stage holds two of the four kx blocks (+ the L row)
+constexpr int kWtStage = kWtHalf + kLRow;
+constexpr int kWtStages = 3;
 constexpr int kA2Row = kW * 16;                   // DEM operand of one row: [512 px][8] = 8 KB
 constexpr int kDemRow = 2176;                     // fp32 DEM halo row (514 floats), 128-byte aligned
 constexpr int kZero = 2048;
@@ -236,12 +237,14 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
         for (int i = 0; i < it.rows + 2; ++i) {
           const int y = it.y0 - 1 + i;
           if (y < 0 || y >= p.H) continue;
-          wait_relaxed(&wt_empty[st], ph);
-          mbar_expect_tx(&wt_full[st], kWtStage);
-          uint8_t* dst = smem_wt + st * kWtStage;
-          bulk_load_1d(dst, reinterpret_cast<const uint8_t*>(p.wt) + (size_t)(y & (kUp - 1)) * kWtRow, kWtRow, &wt_full[st]);
-          tma_load_5d(dst + kWtRow, &tmL, &wt_full[st], 0, 0, y / kUp, it.img, 0);
-          if (++st == kWtStages) { st = 0; ph ^= 1; }
+          for (int h = 0; h < 2; ++h) {
+            wait_relaxed(&wt_empty[st], ph);
+            mbar_expect_tx(&wt_full[st], kWtStage);
+            uint8_t* dst = smem_wt + st * kWtStage;
+            bulk_load_1d(dst, reinterpret_cast<const uint8_t*>(p.wt) + (size_t)(y & (kUp - 1)) * kWtRow + h * kWtHalf, kWtHalf, &wt_full[st]);
+            tma_load_5d(dst + kWtHalf, &tmL, &wt_full[st], 0, 0, y / kUp, it.img, 0);
+            if (++st == kWtStages) { st = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -256,24 +259,27 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
       for (int i = 0; i < it.rows + 2; ++i) {
         const int y = it.y0 - 1 + i;
         if (y < 0 || y >= p.H) continue;
-        mbar_wait(&wt_full[st], ph);
-        mbar_wait(d_empty, dph);
-        tc_fence_after();
-        if (leader) {
-          const uint32_t wbase = wt0 + st * kWtStage;
-          const uint32_t b0 = dlo(wbase + kWtRow, kCells * 16);          // L: [4 planes][32 cells][16 B]
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&wt_full[st], ph);
+          if (h == 0) mbar_wait(d_empty, dph);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t wbase = wt0 + st * kWtStage;
+            const uint32_t b0 = dlo(wbase + kWtHalf, kCells * 16);          // L: [4 planes][32 cells][16 B]
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const uint32_t a0 = dlo(wbase + b * (4 * 2048), 2048);        // block b: [4 planes][128 rows][16 B]
-            umma2(tmem_base + kDcol + b * kCells, a0, b0, desc_hi, idesc, 0u);
-            umma2(tmem_base + kDcol + b * kCells, a0 + ((2 * 2048) >> 4), b0 + ((2 * kCells * 16) >> 4), desc_hi, idesc, 1u);
+            for (int bb = 0; bb < 2; ++bb) {
+              const uint32_t a0 = dlo(wbase + bb * (4 * 2048), 2048);        // block 2 h + bb: [4 planes][128 rows][16 B]
+              const uint32_t dcol = tmem_base + kDcol + (2 * h + bb) * kCells;
+              umma2(dcol, a0, b0, desc_hi, idesc, 0u);
+              umma2(dcol, a0 + ((2 * 2048) >> 4), b0 + ((2 * kCells * 16) >> 4), desc_hi, idesc, 1u);
+            }
+            commit_to(smem_u32(&wt_empty[st]));
+            if (h == 1) commit_to(smem_u32(d_full));
           }
-          commit_to(smem_u32(&wt_empty[st]));
-          commit_to(smem_u32(d_full));
+          __syncwarp();
+          if (++st == kWtStages) { st = 0; ph ^= 1; }
         }
-        __syncwarp();
         dph ^= 1;
-        if (++st == kWtStages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp >= 12 && warp < 20) {
