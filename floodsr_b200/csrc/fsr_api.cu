@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 
 #include "fsr_engine.cuh"
@@ -598,8 +599,8 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   e.d_halo[1].ensure((size_t)T * W * sizeof(float));
   std::vector<cudaEvent_t> ev_in(n_bands), ev_done(n_bands);
   for (int b = 0; b < n_bands; ++b) {
-    FSR_CUDA(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
-    FSR_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+    FSR_CUDA(cudaEventCreateWithFlags(&ev_in[b], getenv("FSR_RASTER_TIMING") ? cudaEventDefault : cudaEventDisableTiming));
+    FSR_CUDA(cudaEventCreateWithFlags(&ev_done[b], getenv("FSR_RASTER_TIMING") ? cudaEventDefault : cudaEventDisableTiming));
   }
   struct EvGuard {
     std::vector<cudaEvent_t>&a, &b;
@@ -608,6 +609,14 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
       for (auto x : b) cudaEventDestroy(x);
     }
   } guard{ev_in, ev_done};
+  const bool timing = getenv("FSR_RASTER_TIMING") != nullptr;
+  const auto h0 = std::chrono::steady_clock::now();
+  double h_enq_in = 0, h_band[16] = {0};
+  cudaEvent_t t_start = nullptr, t_in = nullptr, t_comp = nullptr, t_out = nullptr;
+  if (timing) {
+    for (cudaEvent_t* ev : {&t_start, &t_in, &t_comp, &t_out}) FSR_CUDA(cudaEventCreate(ev));
+    FSR_CUDA(cudaEventRecord(t_start, si));
+  }
   // all input copies are queued up front, in band order
   FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, (size_t)Hl * Wl * sizeof(float), cudaMemcpyHostToDevice, si));
   int copied = 0;
@@ -621,6 +630,7 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
     }
     FSR_CUDA(cudaEventRecord(ev_in[b], si));
   }
+  h_enq_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
   for (int b = 0; b < n_bands; ++b) {
     const int ty0 = band_ty[b], ty1 = band_ty[b + 1];
     FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[b], 0));
@@ -634,10 +644,34 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
     if (e.band.n_rows > 0)
       FSR_CUDA(cudaMemcpyAsync(out_sr + (size_t)e.band.row0 * W, e.d_out.as<float>() + (size_t)e.band.row0 * W,
                                (size_t)e.band.n_rows * W * sizeof(float), cudaMemcpyDeviceToHost, so));
+    if (b < 16) h_band[b] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
   }
   if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)ny * nx * 3 * sizeof(float), cudaMemcpyDeviceToHost, sc_));
+  if (timing) {
+    FSR_CUDA(cudaEventRecord(t_in, si));
+    FSR_CUDA(cudaEventRecord(t_comp, sc_));
+    FSR_CUDA(cudaEventRecord(t_out, so));
+  }
   unsigned f = e.fetch_flags(sc_);
   FSR_CUDA(cudaStreamSynchronize(so));
+  if (timing) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, t_start, t_in);
+    cudaEventElapsedTime(&b, t_start, t_comp);
+    cudaEventElapsedTime(&c, t_start, t_out);
+    fprintf(stderr, "[fsr_run_raster] %d bands: H2D done %.2f ms, kernels done %.2f ms, D2H done %.2f ms | host: inputs queued %.2f, bands queued",
+            n_bands, a, b, c, h_enq_in);
+    for (int k = 0; k < n_bands && k < 16; ++k) fprintf(stderr, " %.2f", h_band[k]);
+    fprintf(stderr, " ms | per band (H2D done, kernels done):");
+    for (int k = 0; k < n_bands; ++k) {
+      float x = 0, y = 0;
+      cudaEventElapsedTime(&x, t_start, ev_in[k]);
+      cudaEventElapsedTime(&y, t_start, ev_done[k]);
+      fprintf(stderr, " (%.2f, %.2f)", x, y);
+    }
+    fprintf(stderr, "\n");
+    for (cudaEvent_t ev : {t_start, t_in, t_comp, t_out}) cudaEventDestroy(ev);
+  }
   if (out_flags) *out_flags = f;
   if (f) throw Error(FSR_E_ASSERT, "input validation failed on the device (see flags)");
   FSR_API_END()

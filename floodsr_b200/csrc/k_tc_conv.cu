@@ -20,7 +20,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 192;
 
 struct ConvTcParams {
@@ -34,6 +34,7 @@ struct ConvTcParams {
   int act;
   float alpha;
   int half;                // 16-bit format: 0 bf16, 1 fp16
+  int stages;              // TMA ring depth (as many as fit: deep layers are L2-latency bound per K step)
   long long plane;         // pixels per CP8 plane of the output/residual tensors (N_capacity * H * W)
   const __nv_bfloat16* wpack;  // [n_tile][tap][stage][kc][BN][8]
   const float* bias;           // [cout] or nullptr
@@ -49,13 +50,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // their TMA latencies overlap
   const int kABytesMax = p.kc * 128 * 16;
   const int kBBytesMax = p.kc * BN * 16;
-  uint8_t* smem_a = smem_raw;                                   // kStages x a_bytes
-  uint8_t* smem_b = smem_raw + kStages * kABytesMax;            // kStages x b_bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * kBBytesMax);
-  uint64_t* full = bars;                // [kStages]
-  uint64_t* empty = bars + kStages;     // [kStages]
-  uint64_t* accum_full = bars + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  uint8_t* smem_a = smem_raw;                                   // p.stages x a_bytes
+  uint8_t* smem_b = smem_raw + p.stages * kABytesMax;            // p.stages x b_bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * kBBytesMax);
+  uint64_t* full = bars;                // [p.stages]
+  uint64_t* empty = bars + p.stages;     // [p.stages]
+  uint64_t* accum_full = bars + 2 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.ksz * p.ksz;
@@ -78,7 +79,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < kStages; ++i) {
+      for (int i = 0; i < p.stages; ++i) {
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], 1);
       }
@@ -102,8 +103,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int tap = 0; tap < taps; ++tap) {
         const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
         for (int st = 0; st < stages_per_tap; ++st, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], a_bytes + b_bytes);
           const bool second = st >= p.s0;
@@ -122,8 +123,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint64_t db_base = smem_desc_kmajor(smem_u32(smem_b), BN * 16, 128);
     const int kpairs = p.kc / 2;
     for (int it = 0; it < n_iters; ++it) {
-      const int s = it % kStages;
-      const uint32_t ph = (it / kStages) & 1;
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
       const uint64_t da = da_base + (uint64_t)((s * kABytesMax) >> 4);
@@ -491,8 +492,18 @@ inline int grid_for(long long total, int threads = 256) {
 }
 
 template <int BN>
-size_t conv_smem_bytes(int kc) {
-  return (size_t)kStages * (kc * 128 * 16) + (size_t)kStages * (kc * BN * 16) + (2 * kStages + 1) * sizeof(uint64_t) + 16;
+size_t conv_smem_bytes(int kc, int stages) {
+  return (size_t)stages * (kc * 128 * 16) + (size_t)stages * (kc * BN * 16) + (2 * stages + 1) * sizeof(uint64_t) + 16;
+}
+template <int BN>
+int conv_stages(int kc, int n_iters, long long n_ctas) {
+  // few CTAs (deep, narrow levels): one CTA per SM with a deep ring, each K step is L2-latency bound;
+  // many CTAs: keep two or more CTAs per SM so that their prologues and epilogues overlap
+  const size_t budget = n_ctas <= 2 * 148 ? 200 * 1024 : 100 * 1024;
+  int st = (int)(budget / ((size_t)kc * 128 * 16 + (size_t)kc * BN * 16));
+  st = st > kMaxStages ? kMaxStages : st;
+  st = st > n_iters ? n_iters : st;
+  return st < 2 ? 2 : st;
 }
 
 }  // namespace
@@ -578,19 +589,23 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc);
   CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc) : m0;
   const int BN = conv_tc_bn(cout);
+  const int n_iters = ksz * ksz * (p.s0 + p.s1);
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)ceil_div(cout, BN));
   if (BN == 128) {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<128>(8))); attr = true; }
-    conv_tc_kernel<128><<<grid, kConvThreads, conv_smem_bytes<128>(kc), s>>>(m0, m1, p);
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
+    p.stages = conv_stages<128>(kc, n_iters, (long long)grid.x * grid.y);
+    conv_tc_kernel<128><<<grid, kConvThreads, conv_smem_bytes<128>(kc, p.stages), s>>>(m0, m1, p);
   } else if (BN == 64) {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<64>(8))); attr = true; }
-    conv_tc_kernel<64><<<grid, kConvThreads, conv_smem_bytes<64>(kc), s>>>(m0, m1, p);
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
+    p.stages = conv_stages<64>(kc, n_iters, (long long)grid.x * grid.y);
+    conv_tc_kernel<64><<<grid, kConvThreads, conv_smem_bytes<64>(kc, p.stages), s>>>(m0, m1, p);
   } else {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes<32>(8))); attr = true; }
-    conv_tc_kernel<32><<<grid, kConvThreads, conv_smem_bytes<32>(kc), s>>>(m0, m1, p);
+    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
+    p.stages = conv_stages<32>(kc, n_iters, (long long)grid.x * grid.y);
+    conv_tc_kernel<32><<<grid, kConvThreads, conv_smem_bytes<32>(kc, p.stages), s>>>(m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
 }

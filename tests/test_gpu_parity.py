@@ -398,3 +398,24 @@ def test_tc_run_raster_matches_oracle_tile_loop(tc_engine, oracle_engine):
     got, got_n, got_summary = tc_engine.run_raster(depth, dem)
     assert got_n == n_tiles and got_summary == summary
     _assert_tc_close(tc_engine, got, want)
+
+
+def test_fused_and_unfused_high_resolution_paths_agree(h1_model_fp, monkeypatch):
+    """The one-kernel convT+head path (k_tc_fused.cu) against the convT -> HBM -> head kernel pair on the same tiles."""
+    from floodsr_b200.engine import EngineB200
+
+    b = 6
+    depth = np.stack([synth_depth(32, 32, seed=80 + i) for i in range(b)])
+    dem = np.stack([synth_dem(512, 512, seed=80 + i) for i in range(b)])
+    fused = EngineB200(h1_model_fp, precision="fp16")
+    monkeypatch.setenv("FSR_NO_FUSED_HR", "1")
+    pair = EngineB200(h1_model_fp, precision="fp16")
+    monkeypatch.delenv("FSR_NO_FUSED_HR")
+    a = fused.run_tiles(depth, dem)
+    c = pair.run_tiles(depth, dem)
+    assert a["dem_stats_used"] == c["dem_stats_used"]
+    # identical 16-bit feature values and weights; only the fp32 accumulation order inside the tensor core differs
+    assert np.abs(a["prediction_norm"] - c["prediction_norm"]).max() <= 2e-6
+    assert np.abs(a["prediction_m"] - c["prediction_m"]).max() <= 2e-5
+    fused.close()
+    pair.close()
