@@ -42,8 +42,10 @@ constexpr int kC = 32;                            // feature channels == head mi
 constexpr int kStrips = 4;                        // 128-pixel strips per 512-pixel row
 constexpr int kW = 512, kCells = 32, kUp = 16;
 constexpr int kRowPx = kW + 2;                    // + zero halo pixel left and right
-constexpr int kFPlane = kRowPx * 16;              // 8224 B: one 8-channel plane of an F row
-constexpr int kFRow = 4 * kFPlane;                // 32896 B
+constexpr int kFPlane = (kRowPx - 1) * 16;        // 8208 B between the 8-channel planes of an F row: the right halo pixel of
+                                                  // one plane shares its slot with the left halo pixel of the next (both are
+                                                  // always zero), which puts the four planes 4 banks apart -> conflict-free stores
+constexpr int kFRow = 32896;                      // stage stride (3 * 8208 + 8224, rounded up to 128 B)
 constexpr int kFStages = 3;
 constexpr int kHwBlocks = 5;                      // [ky2|ky1|ky0|ky2|ky1]
 constexpr int kHwStep = 2 * kHwBlocks * kC * 16;  // one K step of the head weights: [2 planes][160][8] = 5120 B
@@ -289,7 +291,6 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
     const int q = warp & 3;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + kDcol;
     const float bias = p.bias_t[lane];
-    const uint32_t elem_off = (uint32_t)(lane >> 3) * kFPlane + (uint32_t)(lane & 7) * 2;  // channel plane + slot in the 16-byte pixel
     int fs = 0;
     uint32_t fph = 1, dph = 0;
     for (RowIter it(p); it.next();) {
@@ -311,16 +312,18 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(d_empty);
-          uint8_t* dst0 = frow + elem_off + (uint32_t)(1 + 8 * gb + q) * 16;   // pixel 1 + 16 c + 4 b + q, b = 2 gb
+          // lanes 2k / 2k+1 hold channels 2k / 2k+1: one shuffle per cell lets the even lane store the channel pair of block
+          // 2 gb and the odd lane that of block 2 gb + 1 as 32-bit words (32 lanes -> 32 distinct banks)
+          const bool odd = lane & 1;
+          uint8_t* dst0 = frow + (uint32_t)(lane >> 3) * kFPlane + (uint32_t)((lane & 7) >> 1) * 4 +
+                          (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q) * 16;
 #pragma unroll
-          for (int c = 0; c < kCells; c += 2) {
-            const float a0 = act_fn<ACT_T>(v0[c] + bias, p.alpha_t), a1 = act_fn<ACT_T>(v0[c + 1] + bias, p.alpha_t);
-            const float b0 = act_fn<ACT_T>(v1[c] + bias, p.alpha_t), b1 = act_fn<ACT_T>(v1[c + 1] + bias, p.alpha_t);
-            const uint32_t pa = pack_x2(a0, a1, HALF), pb = pack_x2(b0, b1, HALF);
-            *reinterpret_cast<uint16_t*>(dst0 + c * (kUp * 16)) = (uint16_t)pa;
-            *reinterpret_cast<uint16_t*>(dst0 + (c + 1) * (kUp * 16)) = (uint16_t)(pa >> 16);
-            *reinterpret_cast<uint16_t*>(dst0 + c * (kUp * 16) + 64) = (uint16_t)pb;              // block 2 gb + 1: 4 pixels on
-            *reinterpret_cast<uint16_t*>(dst0 + (c + 1) * (kUp * 16) + 64) = (uint16_t)(pb >> 16);
+          for (int c = 0; c < kCells; ++c) {
+            const float a = act_fn<ACT_T>(v0[c] + bias, p.alpha_t);   // block 2 gb, own channel
+            const float b = act_fn<ACT_T>(v1[c] + bias, p.alpha_t);   // block 2 gb + 1, own channel
+            const float other = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
+            const uint32_t w = odd ? pack_x2(other, b, HALF) : pack_x2(a, other, HALF);
+            *reinterpret_cast<uint32_t*>(dst0 + c * (kUp * 16)) = w;
           }
         }
         fence_proxy_async_smem();
