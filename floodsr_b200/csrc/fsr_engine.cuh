@@ -166,6 +166,7 @@ class Engine {
   cudaStream_t s_hd_ = nullptr, s_ct_ = nullptr;
   cudaEvent_t ev_ring_[9] = {};
   DeviceBuf d_big2_;
+  std::vector<char> tc_im_;      // CP8 tensor stored image-major (IM8), maps of <= 64 pixels
   std::vector<char> tc_fmt_;     // 1: CP8 bf16, 0: NHWC fp32
   std::vector<int> tc_cpad_;     // channels as stored
   std::vector<TcOp> tc_ops_;

@@ -15,7 +15,8 @@ namespace fsr {
 int conv_tc_bn(int cout);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
-                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, cudaStream_t s);
+                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
+                    cudaStream_t s);
 bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc);
 void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                          const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
@@ -24,12 +25,13 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
                        int chunks, int half, cudaStream_t s);
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, int half, cudaStream_t s);
+                     long long plane_in, long long plane_out, int half, int im_in, int im_out, cudaStream_t s);
 void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
-                         long long plane_in, long long plane_out, cudaStream_t s);
+                         long long plane_in, long long plane_out, int im_in, int im_out, cudaStream_t s);
 void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
                         int half, cudaStream_t s);
-void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, int half, cudaStream_t s);
+void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, long long plane, int C, int half, int im,
+                        cudaStream_t s);
 void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bfloat16* wpack, const float* bias,
                      __nv_bfloat16* dst, long long plane_out, int n_img, int Hin, int Win, int cin, int cout, int k, int act,
                      float alpha, int half, cudaStream_t s);
@@ -81,9 +83,13 @@ void Engine::tc_prepare(const float* w) {
   const int nt = (int)tensors_.size();
   tc_fmt_.assign(nt, 0);
   tc_cpad_.assign(nt, 0);
+  tc_im_.assign(nt, 0);
   for (int i = 0; i < nt; ++i) {
     tc_fmt_[i] = tensors_[i].c >= 8 ? 1 : 0;  // 1: CP8 bf16, 0: NHWC fp32 (1-channel rasters)
     tc_cpad_[i] = tc_fmt_[i] ? round_up(tensors_[i].c, 16) : tensors_[i].c;
+    // maps of <= 64 pixels are stored image-major (IM8): a conv tap is then one contiguous run per channel chunk instead
+    // of hundreds of 32-byte TMA box rows
+    tc_im_[i] = (tc_fmt_[i] && !big_[i] && tensors_[i].h * tensors_[i].w <= 64 && !getenv("FSR_NO_IM8")) ? 1 : 0;
   }
   tc_ops_.clear();
   tc_ops_.resize(ops_.size());
@@ -120,7 +126,7 @@ void Engine::tc_prepare(const float* w) {
         // wide, shallow levels run the persistent row-box kernel, which works on 32-channel groups
         const auto& d = tensors_[op.dst];
         const int kc_rows = kc > 4 ? 4 : kc;
-        if (!getenv("FSR_NO_CONV_ROWS") && conv_rows_ok(d.h, d.w, op.k, op.cout, C0, C1, kc_rows)) {
+        if (!getenv("FSR_NO_CONV_ROWS") && !tc_im_[op.dst] && conv_rows_ok(d.h, d.w, op.k, op.cout, C0, C1, kc_rows)) {
           kc = kc_rows;
           t.rows = true;
         }
@@ -382,22 +388,24 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
                               cp8(op.dst), tc_plane(op.dst), n, td.h, td.w, op.cout, op.act, op.alpha, half, n_sms_, s);
         else
           launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
-                         tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, s);
+                         tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, tc_im_[op.dst], s);
         break;
       }
       case FSR_OP_POOL:
         if (tc_fmt_[op.src0])
           launch_pool_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, op.mode, tc_plane(op.src0),
-                          tc_plane(op.dst), half, s);
+                          tc_plane(op.dst), half, tc_im_[op.src0], tc_im_[op.dst], s);
         else
           launch_pool_fp32(f32(op.src0), f32(op.dst), n, ts.h, ts.w, ts.c, op.k, op.mode, s);
         break;
       case FSR_OP_UPSAMPLE:
-        launch_upsample_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst), s);
+        launch_upsample_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst),
+                            tc_im_[op.src0], tc_im_[op.dst], s);
         break;
       case FSR_OP_ELTWISE: {
         // planes are strided by capacity: run plane by plane over the live pixels
-        const long long live = (long long)n * td.h * td.w;
+        // IM8 planes interleave the images: process the whole allocated plane there
+        const long long live = tc_im_[op.dst] ? tc_plane(op.dst) : (long long)n * td.h * td.w;
         for (int c8 = 0; c8 < tc_cpad_[op.dst] / 8; ++c8) {
           const size_t o = (size_t)c8 * tc_plane(op.dst) * 8;
           launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, half, s);
@@ -431,7 +439,8 @@ void Engine::debug_read_tensor(int tid, int n_tiles, float* d_out, cudaStream_t 
   const auto& t = tensors_[tid];
   const long long n_pix = (long long)n_tiles * t.h * t.w;
   if (precision_ != FSR_PREC_FP32 && tc_fmt_[tid]) {
-    launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(tbase_[tid]), d_out, n_pix, tc_plane(tid), t.c, precision_ == FSR_PREC_FP16 ? 1 : 0, s);
+    launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(tbase_[tid]), d_out, n_tiles, t.h, t.w, tc_plane(tid), t.c,
+                       precision_ == FSR_PREC_FP16 ? 1 : 0, tc_im_[tid], s);
   } else {
     FSR_CUDA(cudaMemcpyAsync(d_out, tbase_[tid], (size_t)n_pix * t.c * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }

@@ -35,6 +35,9 @@ struct ConvTcParams {
   float alpha;
   int half;                // 16-bit format: 0 bf16, 1 fp16
   int stages;              // TMA ring depth (as many as fit: deep layers are L2-latency bound per K step)
+  int im;                  // 1: image-major tensors ("IM8" [C/8][H*W][N][8], maps of <= 64 pixels): an M tile is 128 images at
+                           // one output pixel, each tap is ONE contiguous 2 KB run per channel chunk, out-of-range taps are skipped
+  int ncap;                // images per pixel plane of IM8 tensors (allocation capacity)
   long long plane;         // pixels per CP8 plane of the output/residual tensors (N_capacity * H * W)
   const __nv_bfloat16* wpack;  // [n_tile][tap][stage][kc][BN][8]
   const float* bias;           // [cout] or nullptr
@@ -65,13 +68,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t a_bytes = (uint32_t)p.kc * 128u * 16u;
   const uint32_t b_bytes = (uint32_t)p.kc * BN * 16u;
 
-  // tile coordinates
+  // tile coordinates (IM8: tx = output pixel x, ty = output pixel y, tn = tile of 128 images)
   int t = blockIdx.x;
   const int tx = t % p.tiles_x;
   t /= p.tiles_x;
   const int ty = t % p.tiles_y;
   const int tn = t / p.tiles_y;
   const int n_tile = blockIdx.y;
+  auto tap_ok = [&](int tap) {
+    if (!p.im) return true;
+    const int pad = p.ksz / 2;
+    const int y = ty + tap / p.ksz - pad, x = tx + tap % p.ksz - pad;
+    return y >= 0 && y < p.H && x >= 0 && x < p.W;
+  };
+  int n_taps_ok = 0;
+  for (int tap = 0; tap < taps; ++tap) n_taps_ok += tap_ok(tap) ? 1 : 0;
+  const int n_iters_cta = n_taps_ok * stages_per_tap;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -101,6 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int pad = p.ksz / 2;
       int it = 0;
       for (int tap = 0; tap < taps; ++tap) {
+        if (!tap_ok(tap)) continue;
         const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
         for (int st = 0; st < stages_per_tap; ++st, ++it) {
           const int s = it % p.stages;
@@ -110,7 +123,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const bool second = st >= p.s0;
           const CUtensorMap* tm = second ? &tmA1 : &tmA0;
           const int chunk0 = (second ? st - p.s0 : st) * p.kc;
-          tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 0, tx * p.bw + dx, ty * p.bh + dy, tn * p.bn, chunk0);
+          if (p.im) tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 0, tn * 128, (ty + dy) * p.W + tx + dx, 0, chunk0);
+          else tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 0, tx * p.bw + dx, ty * p.bh + dy, tn * p.bn, chunk0);
           const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)p.kc * BN * 8);
           bulk_load_1d(smem_b + s * kBBytesMax, wsrc, b_bytes, &full[s]);
         }
@@ -122,7 +136,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint64_t da_base = smem_desc_kmajor(smem_u32(smem_a), 128 * 16, 128);
     const uint64_t db_base = smem_desc_kmajor(smem_u32(smem_b), BN * 16, 128);
     const int kpairs = p.kc / 2;
-    for (int it = 0; it < n_iters; ++it) {
+    for (int it = 0; it < n_iters_cta; ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(&full[s], ph);
@@ -135,7 +149,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           umma_bf16(tmem_base, da + (uint64_t)((j * 2 * (128 * 16)) >> 4), db + (uint64_t)((j * 2 * (BN * 16)) >> 4), idesc,
                     (it > 0 || j > 0) ? 1u : 0u);
         umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
-        if (it == n_iters - 1) umma_commit(accum_full);
+        if (it == n_iters_cta - 1) umma_commit(accum_full);
       }
       __syncwarp();
     }
@@ -146,9 +160,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int lx = m % p.bw;
     const int ly = (m / p.bw) % p.bh;
     const int ln = m / (p.bw * p.bh);
-    const int n_img = tn * p.bn + ln;
+    const int n_img = p.im ? tn * 128 + m : tn * p.bn + ln;
     const bool valid = n_img < p.N;
-    const long long pix = ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
+    const long long pix = p.im ? ((long long)(ty * p.W + tx) * p.ncap + n_img)
+                               : ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
     mbar_wait(accum_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -388,6 +403,13 @@ __global__ void pack_small_kernel(const float* __restrict__ s0, int c0, const fl
   }
 }
 
+// element offset (in 16-bit elements) of 8-channel chunk `ch`, image `img`, pixel (y, x): CP8 [C/8][N][H][W][8] or, for
+// small maps, IM8 [C/8][H*W][N][8]; `ncap` = images per plane as allocated
+__device__ __forceinline__ long long chunk_off(int im, int ch, long long img, int y, int x, int H, int W, long long ncap) {
+  if (im) return (((long long)ch * H * W + (long long)y * W + x) * ncap + img) * 8;
+  return (((long long)ch * ncap + img) * H * W + (long long)y * W + x) * 8;
+}
+
 __device__ __forceinline__ uint4 x8_max(const uint4& a, const uint4& b, int half) {
   uint4 r;
   if (half) {
@@ -406,55 +428,73 @@ __device__ __forceinline__ uint4 x8_max(const uint4& a, const uint4& b, int half
   return r;
 }
 
-// k x k pooling (stride k) on CP8: one thread per (chunk, output pixel)
+// k x k pooling (stride k): one thread per (chunk, output pixel); source and destination may use different layouts
 __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
-                                int Hin, int Win, int k, int mode, long long plane_in, long long plane_out, int half) {
+                                int Hin, int Win, int k, int mode, long long ncap_in, long long ncap_out, int half, int im_in, int im_out) {
   const int Hout = Hin / k, Wout = Win / k;
   const long long n_out = (long long)n_img * Hout * Wout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i % n_out;
     const int ch = (int)(i / n_out);
-    const int X = (int)(pix % Wout);
-    const long long t2 = pix / Wout;
-    const int Y = (int)(t2 % Hout);
-    const long long img = t2 / Hout;
-    const __nv_bfloat16* base = src + (long long)ch * plane_in * 8;
+    long long pix = i % n_out;
+    int X, Y;
+    long long img;
+    if (im_out) {  // image fastest: coalesced stores in the destination layout
+      img = pix % n_img;
+      pix /= n_img;
+      X = (int)(pix % Wout);
+      Y = (int)(pix / Wout);
+    } else {
+      X = (int)(pix % Wout);
+      const long long t2 = pix / Wout;
+      Y = (int)(t2 % Hout);
+      img = t2 / Hout;
+    }
+    const long long o = chunk_off(im_out, ch, img, Y, X, Hout, Wout, ncap_out);
     if (mode == 0) {
-      uint4 acc = __ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k) * Win + (long long)X * k) * 8));
+      uint4 acc = __ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y * k, X * k, Hin, Win, ncap_in)));
       for (int dy = 0; dy < k; ++dy)
         for (int dx = 0; dx < k; ++dx)
-          acc = x8_max(acc, __ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)), half);
-      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = acc;
+          acc = x8_max(acc, __ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y * k + dy, X * k + dx, Hin, Win, ncap_in))), half);
+      *reinterpret_cast<uint4*>(dst + o) = acc;
     } else {
       float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int dy = 0; dy < k; ++dy)
         for (int dx = 0; dx < k; ++dx) {
           float f[8];
-          unpack_x8(__ldg(reinterpret_cast<const uint4*>(base + ((img * Hin + (long long)Y * k + dy) * Win + (long long)X * k + dx) * 8)), f, half);
+          unpack_x8(__ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y * k + dy, X * k + dx, Hin, Win, ncap_in))), f, half);
 #pragma unroll
           for (int j = 0; j < 8; ++j) s[j] += f[j];
         }
       const float inv = 1.0f / (float)(k * k);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] *= inv;
-      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = pack_x8(s, half);
+      *reinterpret_cast<uint4*>(dst + o) = pack_x8(s, half);
     }
   }
 }
 
 __global__ void upsample_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
-                                    int Hin, int Win, int f, long long plane_in, long long plane_out) {
+                                    int Hin, int Win, int f, long long ncap_in, long long ncap_out, int im_in, int im_out) {
   const int Hout = Hin * f, Wout = Win * f;
   const long long n_out = (long long)n_img * Hout * Wout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i % n_out;
     const int ch = (int)(i / n_out);
-    const int X = (int)(pix % Wout);
-    const long long t2 = pix / Wout;
-    const int Y = (int)(t2 % Hout);
-    const long long img = t2 / Hout;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((long long)ch * plane_in + (img * Hin + Y / f) * Win + X / f) * 8));
-    *reinterpret_cast<uint4*>(dst + ((long long)ch * plane_out + pix) * 8) = v;
+    long long pix = i % n_out;
+    int X, Y;
+    long long img;
+    if (im_out) {
+      img = pix % n_img;
+      pix /= n_img;
+      X = (int)(pix % Wout);
+      Y = (int)(pix / Wout);
+    } else {
+      X = (int)(pix % Wout);
+      const long long t2 = pix / Wout;
+      Y = (int)(t2 % Hout);
+      img = t2 / Hout;
+    }
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y / f, X / f, Hin, Win, ncap_in)));
+    *reinterpret_cast<uint4*>(dst + chunk_off(im_out, ch, img, Y, X, Hout, Wout, ncap_out)) = v;
   }
 }
 
@@ -474,13 +514,18 @@ __global__ void eltwise_cp8_kernel(const __nv_bfloat16* __restrict__ a, const __
   }
 }
 
-// CP8 bf16 -> NHWC fp32 (debug / parity reads of intermediate tensors)
-__global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n_pix, long long plane, int C,
-                                   int half) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * C; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / C;
+// CP8 / IM8 16-bit -> NHWC fp32 (debug / parity reads of intermediate tensors)
+__global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n_img, int H, int W,
+                                   long long ncap, int C, int half, int im) {
+  const long long total = n_img * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
-    const __nv_bfloat16* e = src + ((long long)(c >> 3) * plane + pix) * 8 + (c & 7);
+    long long pix = i / C;
+    const int x = (int)(pix % W);
+    pix /= W;
+    const int y = (int)(pix % H);
+    const long long img = pix / H;
+    const __nv_bfloat16* e = src + chunk_off(im, c >> 3, img, y, x, H, W, ncap) + (c & 7);
     dst[i] = half ? __half2float(*reinterpret_cast<const __half*>(e)) : __bfloat162float(*e);
   }
 }
@@ -540,6 +585,21 @@ CUtensorMap make_cp8_tensor_map(const void* base, int W, int H, int N, int chunk
   return m;
 }
 
+// 5-D tensor map over an IM8 activation tensor [C/8][H*W][ncap][8]: dims (8, ncap, H*W, 1, C/8); box (8, 128, 1, 1, kc) =
+// 128 images at one pixel, kc channel chunks: every chunk is one contiguous 2 KB run.
+CUtensorMap make_im8_tensor_map(const void* base, long long ncap, int HW, int chunks, int kc) {
+  CUtensorMap m;
+  cuuint64_t dims[5] = {8, (cuuint64_t)ncap, (cuuint64_t)HW, 1, (cuuint64_t)chunks};
+  cuuint64_t strides[4] = {16, (cuuint64_t)ncap * 16, (cuuint64_t)HW * ncap * 16, (cuuint64_t)HW * ncap * 16};
+  cuuint32_t box[5] = {8, 128, 1, 1, (cuuint32_t)kc};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(FSR_E_CUDA, "cuTensorMapEncodeTiled (IM8) failed with code " + std::to_string((int)r));
+  return m;
+}
+
 // 3-D tensor map over a 1-channel fp32 raster stack [N][H][W]: box (bw, 1, 1), zero fill outside.
 CUtensorMap make_f32_tensor_map_3d(const void* base, int W, int H, int N, int bw) {
   CUtensorMap m;
@@ -566,13 +626,22 @@ int conv_tc_bn(int cout) { return cout >= 128 ? 128 : (cout >= 64 ? 64 : 32); }
 
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
-                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, cudaStream_t s) {
+                    long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
+                    cudaStream_t s) {
   ConvTcParams p{};
   p.half = half;
   p.H = H; p.W = W; p.N = n_img;
-  conv_tc_tile_box(H, W, p.bw, p.bh, p.bn);
-  p.tiles_x = W / p.bw;
-  p.tiles_y = H / p.bh;
+  p.im = im;
+  p.ncap = (int)(plane_out / ((long long)H * W));
+  if (im) {
+    p.bw = 1; p.bh = 1; p.bn = 128;
+    p.tiles_x = W;
+    p.tiles_y = H;
+  } else {
+    conv_tc_tile_box(H, W, p.bw, p.bh, p.bn);
+    p.tiles_x = W / p.bw;
+    p.tiles_y = H / p.bh;
+  }
   p.ksz = ksz;
   p.kc = kc;
   p.s0 = (C0 / 8) / kc;
@@ -586,8 +655,11 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   p.res = res;
   p.out = dst;
   const int tiles_n = ceil_div(n_img, p.bn);
-  CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc);
-  CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc) : m0;
+  CUtensorMap m0 = im ? make_im8_tensor_map(src0, plane0 / ((long long)H * W), H * W, C0 / 8, kc)
+                      : make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc);
+  CUtensorMap m1 = !src1 ? m0
+                   : im  ? make_im8_tensor_map(src1, plane1 / ((long long)H * W), H * W, C1 / 8, kc)
+                         : make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc);
   const int BN = conv_tc_bn(cout);
   const int n_iters = ksz * ksz * (p.s0 + p.s1);
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)ceil_div(cout, BN));
@@ -660,16 +732,18 @@ void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bf
 }
 
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, int half, cudaStream_t s) {
+                     long long plane_in, long long plane_out, int half, int im_in, int im_out, cudaStream_t s) {
+  const long long ncap_in = plane_in / ((long long)Hin * Win), ncap_out = plane_out / ((long long)(Hin / k) * (Win / k));
   pool_cp8_kernel<<<grid_for((long long)n_img * (Hin / k) * (Win / k) * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, k, mode,
-                                                                                                plane_in, plane_out, half);
+                                                                                                ncap_in, ncap_out, half, im_in, im_out);
   FSR_LAUNCH_CHECK();
 }
 
 void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
-                         long long plane_in, long long plane_out, cudaStream_t s) {
+                         long long plane_in, long long plane_out, int im_in, int im_out, cudaStream_t s) {
+  const long long ncap_in = plane_in / ((long long)Hin * Win), ncap_out = plane_out / ((long long)Hin * f * Win * f);
   upsample_cp8_kernel<<<grid_for((long long)n_img * Hin * f * Win * f * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, f,
-                                                                                                plane_in, plane_out);
+                                                                                                ncap_in, ncap_out, im_in, im_out);
   FSR_LAUNCH_CHECK();
 }
 
@@ -679,8 +753,9 @@ void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfl
   FSR_LAUNCH_CHECK();
 }
 
-void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_pix, long long plane, int C, int half, cudaStream_t s) {
-  cp8_to_nhwc_kernel<<<grid_for(n_pix * C), 256, 0, s>>>(src, dst, n_pix, plane, C, half);
+void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, long long plane, int C, int half, int im,
+                        cudaStream_t s) {
+  cp8_to_nhwc_kernel<<<grid_for(n_img * H * W * C), 256, 0, s>>>(src, dst, n_img, H, W, plane / ((long long)H * W), C, half, im);
   FSR_LAUNCH_CHECK();
 }
 
