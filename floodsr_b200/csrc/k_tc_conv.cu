@@ -23,6 +23,23 @@ namespace {
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 192;
 
+// MMA with the 64-bit shared-memory descriptors given as 32-bit halves: the issuing lane then only does 32-bit adds per
+// instruction (rebuilding 64-bit descriptors per MMA costs more issue time than a narrow MMA takes to execute)
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 da, db;\n"
+      ".reg .pred p;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.u32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo32(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+
 struct ConvTcParams {
   int H, W, N;             // per-image extent and number of images in this launch
   int bw, bh, bn;          // M-tile box (bw*bh*bn == 128)
@@ -133,25 +150,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     const uint32_t idesc = idesc_16(128, BN, p.half);
-    const uint64_t da_base = smem_desc_kmajor(smem_u32(smem_a), 128 * 16, 128);
-    const uint64_t db_base = smem_desc_kmajor(smem_u32(smem_b), BN * 16, 128);
+    const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a), 128 * 16);
+    const uint32_t b_lo0 = desc_lo32(smem_u32(smem_b), BN * 16);
+    const uint32_t a_step = (uint32_t)kABytesMax >> 4, b_step = (uint32_t)kBBytesMax >> 4;
     const int kpairs = p.kc / 2;
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0;
     for (int it = 0; it < n_iters_cta; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      const uint64_t da = da_base + (uint64_t)((s * kABytesMax) >> 4);
-      const uint64_t db = db_base + (uint64_t)((s * kBBytesMax) >> 4);
-      if (elect_one()) {
+      if (leader) {
         // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
         for (int j = 0; j < kpairs; ++j)
-          umma_bf16(tmem_base, da + (uint64_t)((j * 2 * (128 * 16)) >> 4), db + (uint64_t)((j * 2 * (BN * 16)) >> 4), idesc,
-                    (it > 0 || j > 0) ? 1u : 0u);
+          umma_lo(tmem_base, a_lo + j * ((2 * 128 * 16) >> 4), b_lo + j * ((2 * BN * 16) >> 4), kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
         umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
         if (it == n_iters_cta - 1) umma_commit(accum_full);
       }
       __syncwarp();
+      a_lo += a_step;
+      b_lo += b_step;
+      if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -164,10 +183,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool valid = n_img < p.N;
     const long long pix = p.im ? ((long long)(ty * p.W + tx) * p.ncap + n_img)
                                : ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
+    // the residual is fetched while the MMAs still run
+    uint4 resv[BN / 8];
+    if (p.res && valid) {
+#pragma unroll
+      for (int c = 0; c < BN / 8; ++c) {
+        const int co = n_tile * BN + c * 8;
+        if (co < p.cout) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)(co >> 3) * p.plane + pix) * 8));
+      }
+    }
     mbar_wait(accum_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < BN / 8; ++c) {
       float v[8];
       tmem_ld8(taddr + c * 8, v);
@@ -183,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (p.res) {
           float r[8];
-          unpack_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), r, p.half);
+          unpack_x8(resv[c], r, p.half);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] += r[i];
         }
@@ -300,32 +328,37 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ===================== MMA issuer =====================
     const uint32_t idesc = idesc_16(128, BN, p.half);
     mbar_wait(w_full, 0);
-    const uint64_t da_base = smem_desc_kmajor(smem_u32(smem_a), (uint32_t)plane_b, 128);
-    const uint64_t db_base = smem_desc_kmajor(smem_u32(smem_w), BN * 16, 128);
+    const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a), (uint32_t)plane_b);
+    const uint32_t b_lo0 = desc_lo32(smem_u32(smem_w), BN * 16);
+    const uint32_t dx_u = (uint32_t)dx_bytes >> 4, row_u = (uint32_t)p.bw;      // box / image-row strides in 16-byte units
+    const uint32_t kpl_u = (uint32_t)(2 * plane_b) >> 4;                          // one MMA = two channel planes
+    const uint32_t wtap_u = (uint32_t)(groups * p.kc * BN * 16) >> 4, wgrp_u = (uint32_t)(p.kc * BN * 16) >> 4;
     const int kpairs = p.kc / 2;
-    int it = 0, nt = 0;
+    const bool leader = elect_one();
+    int s = 0, nt = 0;
+    uint32_t ph = 0;
     for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++nt) {
       const int ab = nt & 1;
       mbar_wait(&acc_empty[ab], ((nt >> 1) & 1) ^ 1);
       const uint32_t d = tmem_base + ab * BN;
-      for (int g = 0; g < groups; ++g, ++it) {
-        const int s = it % kRowStages;
-        mbar_wait(&full[s], (it / kRowStages) & 1);
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (elect_one()) {
+        if (leader) {
+          const uint32_t a_s = a_lo0 + (uint32_t)s * 3 * dx_u;
+          const uint32_t b_g = b_lo0 + (uint32_t)g * wgrp_u;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3, kx = tap % 3;
-            const uint64_t da = da_base + (uint64_t)(((s * 3 + kx) * dx_bytes + ky * p.bw * 16) >> 4);
-            const uint64_t db = db_base + (uint64_t)((((tap * groups + g) * p.kc) * BN * 16) >> 4);
-            for (int j = 0; j < kpairs; ++j)
-              umma_bf16(d, da + (uint64_t)((j * 2 * plane_b) >> 4), db + (uint64_t)((j * 2 * BN * 16) >> 4), idesc,
-                        (g > 0 || tap > 0 || j > 0) ? 1u : 0u);
+            const uint32_t a_t = a_s + (tap % 3) * dx_u + (tap / 3) * row_u;
+            const uint32_t b_t = b_g + tap * wtap_u;
+            umma_lo(d, a_t, b_t, kDescHi, idesc, (g > 0 || tap > 0) ? 1u : 0u);
+            if (kpairs > 1) umma_lo(d, a_t + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
           }
           umma_commit(&empty[s]);
           if (g == groups - 1) umma_commit(&acc_full[ab]);
         }
         __syncwarp();
+        if (++s == kRowStages) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -338,6 +371,11 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int ab = nt & 1;
       const int img = mt / p.tiles_per_img, ty = mt % p.tiles_per_img;
       const long long pix = ((long long)img * p.H + (ty * p.bh + ly)) * p.W + lx;
+      uint4 resv[BN / 8];  // fetched while the tile's MMAs still run
+      if (p.res) {
+#pragma unroll
+        for (int c = 0; c < BN / 8; ++c) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)c * p.plane + pix) * 8));
+      }
       mbar_wait(&acc_full[ab], (nt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN;
@@ -361,7 +399,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
           if (p.res) {
             float r[8];
-            unpack_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), r, p.half);
+            unpack_x8(resv[c32 * 4 + c], r, p.half);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] += r[i];
           }
