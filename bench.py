@@ -121,9 +121,9 @@ class ClockSampler:
         }
 
 
-def head_traffic_per_launch(flops_per_launch: float):
-    """DRAM bytes (read + write) per launch of the head kernel from the committed ncu capture, scaled to this launch size."""
-    fp = REPO / "profiles" / "head_kernel_ncu.json"
+def head_traffic_per_launch(flops_per_launch: float, fused: bool = True):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed ncu capture, scaled to this launch size."""
+    fp = REPO / "profiles" / ("fused_hr_kernel_ncu.json" if fused else "head_kernel_ncu.json")
     if not fp.exists():
         return None
     rec = json.loads(fp.read_text())
@@ -381,7 +381,7 @@ def main():
         "flops_per_launch": head_flops / max(head_launches, 1),
         "ms_per_launch": head_ms / max(head_launches, 1),
         "launches": head_launches,
-        "traffic": head_traffic_per_launch(head_flops / max(head_launches, 1)),
+        "traffic": head_traffic_per_launch(head_flops / max(head_launches, 1), fused),
         "note": "timed inside the step with CUDA events around each launch; FLOPs = transposed convolution + head of the tiles in the launch",
     }
     if not fused and head_isolated is not None and head_isolated[0] > 0:
