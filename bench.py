@@ -167,7 +167,7 @@ def cpu_reference_rate(model_fp: Path, sample_hw=(2048, 3072), steps: int = 1, w
     }
 
 
-def run_reference(args) -> None:
+def run_reference(args, stdout_fd: int) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -194,20 +194,32 @@ def run_reference(args) -> None:
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line, stdout_fd)
+
+
+def emit(line: dict, stdout_fd: int) -> None:
+    """Print the ONE JSON line on the real stdout (everything else a library writes to fd 1 was sent to stderr)."""
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
     args = parse_args()
+    # libraries (NCCL's version banner, warnings) write to fd 1: park the real stdout and point fd 1 at stderr until the
+    # result line is printed
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, stdout_fd)
         return
 
     import torch
     import torch.distributed as dist
 
     from floodsr_b200 import _lib
-    from floodsr_b200.dist import CudaBandExecutor, plan_bands, run_band_step
+    from floodsr_b200.dist import CudaBandExecutor, plan_bands, run_band_step, run_band_step_host
     from floodsr_b200.engine import EngineB200
     from floodsr_b200.synth import synth_dem, synth_depth
 
@@ -265,11 +277,8 @@ def main():
             # the call a user makes: host arrays in, host array out (H2D + D2H inside)
             eng.run_raster(h_depth, h_dem, window_method="feather", overlap_lr=OVERLAP_LR, out=h_out)
         else:
-            dd = t_dem_host.to(dev, non_blocking=True)
-            dp = t_depth_host.to(dev, non_blocking=True)
-            rows_t = run_band_step(ex, plan, plans, dp, dd, r0, dist_mod, None, d_out)
-            t_out_host.copy_(rows_t, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            # each rank: its rows from pinned host memory, through the engine's copy/compute pipeline, halo via NCCL
+            run_band_step_host(ex, plan, plans, h_depth, h_dem, r0, h_out, dist_mod, None)
 
     def barrier():
         torch.cuda.synchronize()
@@ -435,7 +444,7 @@ def main():
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line, stdout_fd)
     if world > 1:
         dist.destroy_process_group()
 

@@ -109,6 +109,7 @@ Engine::~Engine() {
     b->release();
   win.release();
   d_big2_.release();
+  d_tiles0.release();
   fused_hw_.release();
   fused_wt_.release();
   if (s_hd_) cudaStreamDestroy(s_hd_);
@@ -380,21 +381,25 @@ static void band_rows(const Engine& e, int ty0, int ty1, int& row0, int& n_rows,
 
 // d_depth/d_dem hold raster rows starting at band_row0 (HR rows; band_row0 % scale == 0), band_rows_hr of them.
 static void band_run(Engine& e, const float* d_depth, const float* d_dem, int band_row0, int band_rows_hr, int ty0, int ty1,
-                     const fsr_tile_params& p, float* d_halo_out, float* d_stats, cudaStream_t s) {
+                     const fsr_tile_params& p, float* d_halo_out, float* d_stats, cudaStream_t s, DeviceBuf* tiles_buf = nullptr,
+                     const int2* d_origins = nullptr) {
   const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T;
   FSR_REQUIRE(ty0 >= 0 && ty0 < ty1 && ty1 <= ny, "bad tile-row range");
   FSR_REQUIRE(band_row0 % e.scale() == 0 && band_row0 <= e.win.ys[ty0], "band rows do not cover the band's first window");
   const int need_end = std::min(e.win.ys[ty1 - 1] + T, e.win.H);
   FSR_REQUIRE(band_row0 + band_rows_hr >= need_end, "band rows do not cover the band's last window");
   const int n_tiles = (ty1 - ty0) * nx;
-  e.d_tiles.ensure((size_t)n_tiles * T * T * sizeof(float));
+  DeviceBuf& tiles = tiles_buf ? *tiles_buf : e.d_tiles;
+  tiles.ensure((size_t)n_tiles * T * T * sizeof(float));
   float* stats = d_stats;
   if (!stats) {
     e.d_stats.ensure((size_t)n_tiles * 3 * sizeof(float));
     stats = e.d_stats.as<float>();
   }
   TileGrid grid;
-  if (band_row0 == 0) {
+  if (d_origins) {
+    grid.origins = d_origins;  // uploaded by the caller, relative to band_row0
+  } else if (band_row0 == 0) {
     // the buffers hold the raster from its first row: the global window origins uploaded by setup_windows apply
     grid.origins = e.win.d_origins.as<int2>() + (size_t)ty0 * nx;
   } else {
@@ -415,22 +420,24 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
   grid.Hl = ceil_div(grid.H, e.scale());
   grid.Hl = std::min(grid.Hl, e.win.H / e.scale() - band_row0 / e.scale());
   grid.Wl = e.win.W / e.scale();
-  e.run_tiles_from_grid(d_depth, d_dem, grid, 0, n_tiles, p, e.d_tiles.as<float>(), nullptr, stats, s);
+  e.run_tiles_from_grid(d_depth, d_dem, grid, 0, n_tiles, p, tiles.as<float>(), nullptr, stats, s);
   int row0, n_rows, halo_out;
   band_rows(e, ty0, ty1, row0, n_rows, halo_out);
   e.band = BandState{ty0, ty1, row0, n_rows, halo_out, p.max_depth};
   if (halo_out > 0 && d_halo_out) {
     BlendGeom g = e.blend_geom();
     ProfScope scope(e.prof, PROF_BLEND, s);
-    launch_blend(e.d_tiles.as<float>(), ty0, ty1, g, row0 + n_rows, halo_out, nullptr, 0, false, p.max_depth, d_halo_out, s);
+    launch_blend(tiles.as<float>(), ty0, ty1, g, row0 + n_rows, halo_out, nullptr, 0, false, p.max_depth, d_halo_out, s);
   }
 }
 
-static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s) {
+static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s,
+                          const DeviceBuf* tiles_buf = nullptr, const BandState* st = nullptr) {
   BlendGeom g = e.blend_geom();
+  const BandState& b = st ? *st : e.band;
+  const DeviceBuf& tiles = tiles_buf ? *tiles_buf : e.d_tiles;
   ProfScope scope(e.prof, PROF_BLEND, s);
-  launch_blend(e.d_tiles.as<float>(), e.band.ty0, e.band.ty1, g, e.band.row0, e.band.n_rows, d_halo_in, halo_rows_in, true,
-               e.band.max_depth, d_out_rows, s);
+  launch_blend(tiles.as<float>(), b.ty0, b.ty1, g, b.row0, b.n_rows, d_halo_in, halo_rows_in, true, b.max_depth, d_out_rows, s);
 }
 
 }  // namespace fsr
@@ -719,6 +726,130 @@ int fsr_band_finalize_dev(fsr_engine* eng, const float* d_halo_in, int32_t halo_
   FSR_REQUIRE(d_out_rows != nullptr, "NULL device buffer");
   FSR_REQUIRE(eng->impl.band.ty1 > eng->impl.band.ty0, "fsr_band_run_dev has not been called");
   band_finalize(eng->impl, d_halo_in, halo_rows_in, d_out_rows, (cudaStream_t)stream);
+  FSR_API_END()
+}
+
+// Pipelined host-buffer variant of fsr_band_run_dev + fsr_band_finalize_dev for one rank's band of window rows
+// [ty0, ty1): sub-bands overlap their H2D copy, kernels and D2H copy exactly like fsr_run_raster.  The sub-band that
+// shares rows with the previous rank is finalised last (fsr_band_host_end), after the caller has received that rank's
+// partial sums, so ranks never wait for one another while computing.
+int fsr_band_host_begin(fsr_engine* eng, const float* depth_lr, const float* dem_hr, int32_t band_row0, int32_t band_rows_hr,
+                        int32_t ty0, int32_t ty1, const fsr_tile_params* params, float* out_rows, float* d_halo_out) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  const int T = e.hr_tile(), sc = e.scale();
+  check_params(params, T * T);
+  const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), W = e.win.W, H = e.win.H;
+  FSR_REQUIRE(ny > 0, "fsr_set_windows has not been called");
+  FSR_REQUIRE(depth_lr && dem_hr && out_rows, "NULL host buffer");
+  FSR_REQUIRE(ty0 >= 0 && ty0 < ty1 && ty1 <= ny, "bad tile-row range");
+  FSR_REQUIRE(band_row0 % sc == 0 && band_row0 <= e.win.ys[ty0] && band_row0 + band_rows_hr >= std::min(e.win.ys[ty1 - 1] + T, H),
+              "host rows do not cover the band's windows");
+  e.ensure_streams();
+  cudaStream_t sc_ = e.s_comp, si = e.s_in, so = e.s_out;
+  const int lr0 = band_row0 / sc;
+  const int lr_rows = std::min(ceil_div(band_row0 + band_rows_hr, sc), H / sc) - lr0;
+  const int Wl = W / sc;
+  int rank_row0, rank_rows, rank_halo;
+  band_rows(e, ty0, ty1, rank_row0, rank_rows, rank_halo);
+  e.d_in_depth.ensure((size_t)lr_rows * Wl * sizeof(float));
+  e.d_in_dem.ensure((size_t)band_rows_hr * W * sizeof(float));
+  e.d_out.ensure((size_t)std::max(rank_rows, 1) * W * sizeof(float));
+  e.d_halo[0].ensure((size_t)T * W * sizeof(float));
+  e.d_halo[1].ensure((size_t)T * W * sizeof(float));
+  // window origins relative to the first host row, for all windows of the rank
+  {
+    std::vector<int> org((size_t)(ty1 - ty0) * nx * 2);
+    for (int yi = ty0; yi < ty1; ++yi)
+      for (int xi = 0; xi < nx; ++xi) {
+        org[((size_t)(yi - ty0) * nx + xi) * 2 + 0] = e.win.ys[yi] - band_row0;
+        org[((size_t)(yi - ty0) * nx + xi) * 2 + 1] = e.win.xs[xi];
+      }
+    e.d_tmp_a.ensure(org.size() * sizeof(int));
+    FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, sc_));
+    FSR_CUDA(cudaStreamSynchronize(sc_));
+  }
+  // sub-band plan: single window rows first and last, like fsr_run_raster
+  const int n_rows_rank = ty1 - ty0;
+  int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
+  std::vector<int> band_ty{ty0};
+  if (n_rows_rank >= 3 && rows_per_band > 1) {
+    band_ty.push_back(ty0 + 1);
+    while (band_ty.back() < ty1 - 1) band_ty.push_back(std::min(band_ty.back() + rows_per_band, (int)ty1 - 1));
+  } else {
+    while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
+  }
+  band_ty.push_back(ty1);
+  const int n_bands = (int)band_ty.size() - 1;
+  std::vector<cudaEvent_t> ev_in(n_bands), ev_done(n_bands);
+  for (int b = 0; b < n_bands; ++b) {
+    FSR_CUDA(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
+    FSR_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+  }
+  struct EvGuard {
+    std::vector<cudaEvent_t>&a, &b;
+    ~EvGuard() {
+      for (auto x : a) cudaEventDestroy(x);
+      for (auto x : b) cudaEventDestroy(x);
+    }
+  } guard{ev_in, ev_done};
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_depth.p, depth_lr, (size_t)lr_rows * Wl * sizeof(float), cudaMemcpyHostToDevice, si));
+  int copied = 0;  // host rows copied so far
+  for (int b = 0; b < n_bands; ++b) {
+    const int need = b == n_bands - 1 ? band_rows_hr : std::min(e.win.ys[band_ty[b + 1] - 1] + T, H) - band_row0;
+    if (need > copied) {
+      FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.as<float>() + (size_t)copied * W, dem_hr + (size_t)copied * W,
+                               (size_t)(need - copied) * W * sizeof(float), cudaMemcpyHostToDevice, si));
+      copied = need;
+    }
+    FSR_CUDA(cudaEventRecord(ev_in[b], si));
+  }
+  const bool defer_first = ty0 > 0;  // rows shared with the previous rank: blended in fsr_band_host_end
+  for (int b = 0; b < n_bands; ++b) {
+    const int s0 = band_ty[b], s1 = band_ty[b + 1];
+    const bool last = b == n_bands - 1;
+    FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[b], 0));
+    float* halo_dst = (last && d_halo_out) ? d_halo_out : e.d_halo[b & 1].as<float>();
+    band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), band_row0, band_rows_hr, s0, s1, *params, halo_dst, nullptr, sc_,
+             (b == 0 && defer_first) ? &e.d_tiles0 : nullptr, e.d_tmp_a.as<int2>() + (size_t)(s0 - ty0) * nx);
+    const int halo_in = b == 0 ? 0 : e.band_halo_rows[(b - 1) & 1];
+    e.band_halo_rows[b & 1] = e.band.halo_out_rows;
+    if (b == 0 && defer_first) {
+      e.band0 = e.band;
+      e.band0_out = out_rows;
+      e.band0_rank_row0 = rank_row0;
+    } else {
+      float* d_rows = e.d_out.as<float>() + (size_t)(e.band.row0 - rank_row0) * W;
+      band_finalize(e, b == 0 ? nullptr : e.d_halo[(b - 1) & 1].as<float>(), halo_in, d_rows, sc_);
+      FSR_CUDA(cudaEventRecord(ev_done[b], sc_));
+      FSR_CUDA(cudaStreamWaitEvent(so, ev_done[b], 0));
+      if (e.band.n_rows > 0)
+        FSR_CUDA(cudaMemcpyAsync(out_rows + (size_t)(e.band.row0 - rank_row0) * W, d_rows, (size_t)e.band.n_rows * W * sizeof(float),
+                                 cudaMemcpyDeviceToHost, so));
+    }
+  }
+  e.band0_pending = defer_first;
+  FSR_CUDA(cudaStreamSynchronize(sc_));  // the rank's halo (d_halo_out) is complete; D2H copies may still be in flight
+  FSR_API_END()
+}
+
+int fsr_band_host_end(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows_in, uint32_t* out_flags) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  FSR_REQUIRE(e.s_comp != nullptr, "fsr_band_host_begin has not been called");
+  const int W = e.win.W;
+  if (e.band0_pending) {
+    float* d_rows = e.d_out.as<float>() + (size_t)(e.band0.row0 - e.band0_rank_row0) * W;
+    band_finalize(e, d_halo_in, halo_rows_in, d_rows, e.s_comp, &e.d_tiles0, &e.band0);
+    if (e.band0.n_rows > 0)
+      FSR_CUDA(cudaMemcpyAsync(e.band0_out + (size_t)(e.band0.row0 - e.band0_rank_row0) * W, d_rows,
+                               (size_t)e.band0.n_rows * W * sizeof(float), cudaMemcpyDeviceToHost, e.s_comp));
+    e.band0_pending = false;
+  }
+  unsigned f = e.fetch_flags(e.s_comp);
+  FSR_CUDA(cudaStreamSynchronize(e.s_out));
+  if (out_flags) *out_flags = f;
+  if (f) throw Error(FSR_E_ASSERT, "input validation failed on the device (see flags)");
   FSR_API_END()
 }
 

@@ -143,6 +143,12 @@ class Engine {
     FSR_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
   }
   int band_tiles_target() const { return band_tiles_; }
+  // fsr_band_host_begin/_end: the sub-band sharing rows with the previous rank is blended last
+  DeviceBuf d_tiles0;
+  BandState band0;
+  float* band0_out = nullptr;
+  int band0_rank_row0 = 0;
+  bool band0_pending = false;
 
  private:
   void ensure_arena(int n_tiles);

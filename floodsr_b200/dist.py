@@ -153,10 +153,55 @@ class CudaBandExecutor:
     def make_recv(self, rows: int):
         return self.torch.empty((rows, self.w), dtype=self.torch.float32, device=self.device)
 
+    # -- host-buffer path: the band's H2D copies, kernels and D2H copies overlap inside the engine --------------------
+    def band_host_begin(self, plan: BandPlan, depth_host: np.ndarray, dem_host: np.ndarray, band_row0: int, out_rows: np.ndarray):
+        """Queue the whole band from (page-locked) host arrays; returns this band's halo partial sums (CUDA tensor or None)."""
+        torch = self.torch
+        self.set_windows()
+        assert dem_host.dtype == np.float32 and dem_host.flags["C_CONTIGUOUS"] and dem_host.shape[1] == self.w
+        assert depth_host.dtype == np.float32 and depth_host.flags["C_CONTIGUOUS"]
+        assert out_rows.dtype == np.float32 and out_rows.flags["C_CONTIGUOUS"] and out_rows.shape == (plan.n_rows, self.w)
+        halo = None
+        if plan.halo_out_rows > 0:
+            halo = torch.empty((plan.halo_out_rows, self.w), dtype=torch.float32, device=self.device)
+        self._lib_mod.check(
+            self.lib.fsr_band_host_begin(
+                self.engine._handle, self._lib_mod.fptr(depth_host), self._lib_mod.fptr(dem_host), int(band_row0),
+                int(dem_host.shape[0]), plan.ty0, plan.ty1, C.byref(self.params), self._lib_mod.fptr(out_rows),
+                C.c_void_p(halo.data_ptr()) if halo is not None else None,
+            )
+        )
+        return halo
+
+    def band_host_end(self, halo_in):
+        """Blend the rows shared with the previous band (its partial sums in `halo_in`), wait for the copies."""
+        flags = C.c_uint32(0)
+        code = self.lib.fsr_band_host_end(
+            self.engine._handle, C.c_void_p(halo_in.data_ptr()) if halo_in is not None else None,
+            int(halo_in.shape[0]) if halo_in is not None else 0, C.byref(flags),
+        )
+        if code == self._lib_mod.FSR_E_ASSERT:
+            self.engine._raise_flags(int(flags.value), True, None)
+        self._lib_mod.check(code)
+
     def check_flags(self):
         flags = C.c_uint32(0)
         self._lib_mod.check(self.lib.fsr_fetch_flags(self.engine._handle, self._stream(), C.byref(flags)))
         self.engine._raise_flags(int(flags.value), True, None)
+
+
+def run_band_step_host(executor, plan: BandPlan, plans: list[BandPlan], depth_host, dem_host, band_row0: int, out_rows,
+                       dist_mod=None, group=None):
+    """`run_band_step` from / to host arrays (page-locked for full overlap): copies are pipelined with the kernels."""
+    if plan.empty:
+        return None
+    halo_out = executor.band_host_begin(plan, depth_host, dem_host, band_row0, out_rows)
+    halo_in = None
+    if dist_mod is not None and len(plans) > 1:
+        halo_in = exchange_halo(plan, plans, halo_out, executor.make_recv, dist_mod, group)
+        executor.torch.cuda.current_stream(executor.device).synchronize()
+    executor.band_host_end(halo_in)
+    return out_rows
 
 
 def run_band_step(executor, plan: BandPlan, plans: list[BandPlan], depth_band, dem_band, band_row0: int, dist_mod=None, group=None, out_rows=None):

@@ -144,6 +144,17 @@ int fsr_band_run_dev(fsr_engine* eng, const float* d_depth_lr, const float* d_de
                      float* d_halo_out, float* d_stats, void* stream);
 int fsr_band_finalize_dev(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows_in, float* d_out_rows,
                           void* stream);
+/* Host-buffer, pipelined variant for one rank's band (new; used by bench.py's multi-GPU end-to-end leg and by
+ * floodsr_b200/dist.py): depth_lr / dem_hr / out_rows are (page-locked) host buffers holding the raster rows from HR row
+ * band_row0 on and the rows the band owns; sub-bands overlap H2D, kernels and D2H like fsr_run_raster.
+ *   fsr_band_host_begin  queues everything except the blend of the rows shared with the previous rank, writes the rows
+ *                        shared with the next rank as partial sums to d_halo_out (device, may be NULL for the last rank)
+ *                        and returns when those are complete.
+ *   fsr_band_host_end    after the caller has received the previous rank's partial sums into d_halo_in (device, NULL for
+ *                        the first rank): blends the deferred rows, waits for all copies, reports the assertion flags. */
+int fsr_band_host_begin(fsr_engine* eng, const float* depth_lr, const float* dem_hr, int32_t band_row0, int32_t band_rows_hr,
+                        int32_t ty0, int32_t ty1, const fsr_tile_params* params, float* out_rows, float* d_halo_out);
+int fsr_band_host_end(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows_in, uint32_t* out_flags);
 /* Poll and clear the assertion flags raised by _dev calls (synchronises `stream`). */
 int fsr_fetch_flags(fsr_engine* eng, void* stream, uint32_t* out_flags);
 

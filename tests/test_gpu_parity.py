@@ -419,3 +419,32 @@ def test_fused_and_unfused_high_resolution_paths_agree(h1_model_fp, monkeypatch)
     assert np.abs(a["prediction_m"] - c["prediction_m"]).max() <= 2e-5
     fused.close()
     pair.close()
+
+
+@pytest.mark.parametrize("h,w,world", [(2048, 1024, 2), (4096, 1024, 3)])
+def test_band_host_pipeline_is_bit_identical_to_single_pass(tc_engine, h, w, world):
+    """Host-buffer band path (pipelined copies, deferred blend of the rows shared with the previous rank)."""
+    from floodsr_b200 import _lib
+    from floodsr_b200.dist import CudaBandExecutor, plan_bands
+
+    depth, dem = synth_raster(h, w, seed=h + 1)
+    want, _, _ = tc_engine.run_raster(depth, dem)
+    plans, ys, xs = plan_bands(h, w, 512, "feather", 128, world)
+    ex = CudaBandExecutor(tc_engine, h, w, "feather", 128)
+    got = np.empty_like(want)
+    halo = None
+    for plan in plans:
+        if plan.empty:
+            continue
+        r0 = plan.in_row0
+        dem_band = _lib.pinned_empty((plan.in_rows, w))
+        dem_band[:] = dem[r0 : r0 + plan.in_rows]
+        lr0, lr1 = r0 // 16, min((r0 + plan.in_rows + 15) // 16, h // 16)
+        depth_band = _lib.pinned_empty((lr1 - lr0, w // 16))
+        depth_band[:] = depth[lr0:lr1]
+        out_rows = _lib.pinned_empty((plan.n_rows, w))
+        halo_out = ex.band_host_begin(plan, depth_band, dem_band, r0, out_rows)
+        ex.band_host_end(halo)
+        got[plan.row0 : plan.row0 + plan.n_rows] = out_rows
+        halo = halo_out
+    assert np.array_equal(got, want)
