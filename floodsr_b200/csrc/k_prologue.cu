@@ -24,7 +24,7 @@ constexpr int kDigitBits = 11;
 constexpr int kBinsPerThread = kBins / kThreads;
 constexpr int kWarps = kThreads / 32;
 constexpr int kCap = 22528;        // compacted upper-tail keys kept in shared memory (88 KB)
-constexpr int kSampleStep = 8;     // every 8th float4 of the tile feeds the threshold estimate
+constexpr int kSampleRows = 16;    // every 16th tile row feeds the threshold estimate
 constexpr int kUnroll = 4;         // independent loads in flight per thread in the streaming passes
 
 struct SelState {
@@ -210,19 +210,28 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   // threshold estimated from a 1/8 sample lets ONE full pass compact every key >= threshold into shared memory
   // (exact count checked afterwards), where the exact radix select runs without touching the tile again.
   const int n_top = n_px - p.rank_lo;
-  const bool try_fast = own_stats && (long long)n_top * 14 / 10 + 2048 <= kCap && T % (4 * kSampleStep) == 0;
+  const bool try_fast = own_stats && (long long)n_top * 14 / 10 + 2048 <= kCap && T % kSampleRows == 0 &&
+                        (T / kSampleRows) * T <= kCap && ((T / kSampleRows) * vec_per_row) % kThreads == 0;
   unsigned thr_key = 0;
   if (try_fast) {
-    // sample min / max
+    // one coalesced read of every kSampleRows-th tile row (6 % of the tile) into shared memory; min / max and the
+    // histogram of the sample are then formed from there
+    const int n_srows = T / kSampleRows, n_samp = n_srows * T;
     float smin = INFINITY, smax = 0.0f;
     unsigned dummy = 0;
-    for (int i = t * kSampleStep; i < n_vec; i += kThreads * kSampleStep) {
-      int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-      float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
-      float a = fmaxf(fix_dem(v.x, p, dummy), 0.0f), b = fmaxf(fix_dem(v.y, p, dummy), 0.0f);
-      float cc = fmaxf(fix_dem(v.z, p, dummy), 0.0f), d = fmaxf(fix_dem(v.w, p, dummy), 0.0f);
-      smin = fminf(smin, fminf(fminf(a, b), fminf(cc, d)));
-      smax = fmaxf(smax, fmaxf(fmaxf(a, b), fmaxf(cc, d)));
+    for (int i = t; i < n_srows * vec_per_row; i += kThreads) {
+      const int sr = i / vec_per_row, c = (i - sr * vec_per_row) * 4;
+      const float4 v = load4(dem, grid.H, grid.W, org.x + sr * kSampleRows + kSampleRows / 2, org.y + c);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      unsigned k[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float f = fmaxf(fix_dem(e[j], p, dummy), 0.0f) + 0.0f;
+        smin = fminf(smin, f);
+        smax = fmaxf(smax, f);
+        k[j] = __float_as_uint(f);
+      }
+      *reinterpret_cast<uint4*>(&s_keys[4 * i]) = make_uint4(k[0], k[1], k[2], k[3]);
     }
     smin = warp_min(smin);
     smax = warp_max(smax);
@@ -238,27 +247,20 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
       smin = fminf(smin, red_min[w]);
       smax = fmaxf(smax, red_max[w]);
     }
-    const unsigned klo = __float_as_uint(smin + 0.0f), khi = __float_as_uint(smax + 0.0f);
+    const unsigned klo = __float_as_uint(smin), khi = __float_as_uint(smax);
     if (khi > klo) {
       const int sh = digit_shift(klo, khi);
-      for (int i = t * kSampleStep; i < n_vec; i += kThreads * kSampleStep) {
-        int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-        float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
-        float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(&hist[0][(dem_key(e[j], p, dummy) - klo) >> sh], 1);
-      }
+      for (int i = t; i < n_samp; i += kThreads) atomicAdd(&hist[0][(s_keys[i] - klo) >> sh], 1);
       __syncthreads();
-      // rank (from below) of the sample element above which ~1.3 x n_top / 8 samples lie
-      const int n_samp = n_px / kSampleStep;
-      const int want_above = (int)(((long long)n_top * 13 / 10 + 512) / kSampleStep);
+      // rank (from below) of the sample element above which ~1.3 x n_top / kSampleRows samples lie
+      const int want_above = (int)(((long long)n_top * 13 / 10 + 512) / kSampleRows);
       const int srank = n_samp - 1 - want_above;
       if (srank > 0) {
         find_bin(hist[0], srank, warp_tot, &sel_bin, &sel_before);
         thr_key = klo + ((unsigned)sel_bin << sh);  // lower edge of that sample bin
       }
     }
-    __syncthreads();  // hist / red arrays are reused below
+    __syncthreads();  // hist / red arrays and the key buffer are reused below
   }
 
   // ---- pass A: min / max of clip(x, 0, inf), finite checks, compaction of the upper tail ------------

@@ -238,7 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 //     are row offsets (bw * 16 B) into a box, so the L2 -> shared-memory traffic is 3 boxes instead of 9;
 //   * accumulators are double-buffered in TMEM, so the epilogue of tile t overlaps the MMAs of tile t + 1, and the
 //     per-CTA set-up (TMEM allocation, barrier init, first TMA latency) is paid once per SM instead of once per tile.
-constexpr int kRowStages = 3;
+constexpr int kRowMaxStages = 6;
 
 struct ConvRowsParams {
   int H, W, N;
@@ -250,6 +250,7 @@ struct ConvRowsParams {
   int cout, act;
   float alpha;
   int half;
+  int stages;          // halo-box ring depth (as many as fit beside the weights: the kernel is fetch-latency bound)
   long long plane;     // pixels per CP8 plane of the output/residual tensors
   const __nv_bfloat16* wpack;  // [tap][group][kc][BN][8]
   int w_bytes;
@@ -266,12 +267,12 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int dx_bytes = p.kc * plane_b;               // one box
   const int w_round = (p.w_bytes + 1023) & ~1023;
   uint8_t* smem_w = smem_raw;
-  uint8_t* smem_a = smem_raw + w_round;              // kRowStages x 3 boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kRowStages * 3 * dx_bytes);
+  uint8_t* smem_a = smem_raw + w_round;              // p.stages x 3 boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * 3 * dx_bytes);
   uint64_t* w_full = bars;
-  uint64_t* full = bars + 1;                 // [kRowStages]
-  uint64_t* empty = full + kRowStages;       // [kRowStages]
-  uint64_t* acc_full = empty + kRowStages;   // [2]
+  uint64_t* full = bars + 1;                 // [p.stages]
+  uint64_t* empty = full + p.stages;       // [p.stages]
+  uint64_t* acc_full = empty + p.stages;   // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -285,7 +286,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(w_full, 1);
-      for (int i = 0; i < kRowStages; ++i) {
+      for (int i = 0; i < p.stages; ++i) {
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], 1);
       }
@@ -313,8 +314,8 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
         const int img = mt / p.tiles_per_img, ty = mt % p.tiles_per_img;
         for (int g = 0; g < groups; ++g, ++it) {
-          const int s = it % kRowStages;
-          mbar_wait(&empty[s], ((it / kRowStages) & 1) ^ 1);
+          const int s = it % p.stages;
+          mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
           mbar_expect_tx(&full[s], 3u * (uint32_t)dx_bytes);
           const bool second = g >= p.g0;
           const CUtensorMap* tm = second ? &tmA1 : &tmA0;
@@ -358,7 +359,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (g == groups - 1) umma_commit(&acc_full[ab]);
         }
         __syncwarp();
-        if (++s == kRowStages) { s = 0; ph ^= 1; }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -728,7 +729,7 @@ bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc) {
   if (H % bh) return false;
   if (kc != 2 && kc != 4) return false;
   const size_t w_bytes = (size_t)9 * ((C0 + C1) / 8) * cout * 16;
-  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + (size_t)kRowStages * 3 * kc * (bh + 2) * W * 16 + 256;
+  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + (size_t)3 * 3 * kc * (bh + 2) * W * 16 + 256;  // >= 3 stages
   return smem <= 200 * 1024;
 }
 
@@ -751,7 +752,9 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   p.bias = bias; p.res = res; p.out = dst;
   CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh + 2, 1, kc);
   CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh + 2, 1, kc) : m0;
-  const size_t smem = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023) + (size_t)kRowStages * 3 * kc * (p.bh + 2) * W * 16 + 256;
+  const size_t w_round = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023), stage_bytes = (size_t)3 * kc * (p.bh + 2) * W * 16;
+  p.stages = (int)std::min<size_t>(kRowMaxStages, (200 * 1024 - 256 - w_round) / stage_bytes);
+  const size_t smem = w_round + (size_t)p.stages * stage_bytes + 256;
   const int grid = p.n_mtiles < n_sms ? p.n_mtiles : n_sms;
   if (cout == 64) {
     FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
