@@ -59,13 +59,15 @@ def parse_args():
 def find_model(tmpdir: Path) -> tuple[Path, str]:
     """The reference's lookup order (tests/conftest.py:200-215): ./_inputs/<ver>/*.onnx, then the user cache; else random init."""
     from floodsr_b200.h1 import write_h1_model
+    from floodsr_b200.model_store import find_model as locate_model
 
     ver = "ResUNet_16x_DEM"
-    for cand in [REPO / "_inputs" / ver, Path.home() / ".cache" / "floodsr" / ver]:
-        if cand.exists():
-            hits = sorted(cand.glob("*.onnx"))
-            if hits and hits[0].stat().st_size > 1_000_000:
-                return hits[0], "model_infer.onnx (release asset)"
+    try:
+        hit = locate_model(ver, inputs_dir=REPO / "_inputs")
+    except ValueError:
+        hit = None  # a cached file that is not the release asset
+    if hit is not None and hit.stat().st_size > 1_000_000:
+        return hit, "model_infer.onnx (release asset)"
     return write_h1_model(tmpdir / ver / "model_infer.onnx", seed=0), "random-init H1 graph (12,045,568 parameters; release asset unavailable offline)"
 
 
