@@ -448,3 +448,15 @@ def test_band_host_pipeline_is_bit_identical_to_single_pass(tc_engine, h, w, wor
         got[plan.row0 : plan.row0 + plan.n_rows] = out_rows
         halo = halo_out
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("h,w,method", [(160, 208, "feather"), (528, 1296, "hard"), (1024, 512, "feather")])
+def test_tc_run_raster_ragged_and_hard(tc_engine, oracle_engine, h, w, method):
+    """Rasters smaller than / not a multiple of the tile (virtual zero padding) and the hard mosaic in the 16-bit modes."""
+    from oracle.stitch_np import run_tiled
+
+    depth, dem = synth_raster(h, w, seed=h * 3 + w)
+    want, n_tiles, summary = run_tiled(oracle_engine, depth, dem, window_method=method, overlap_lr=8)
+    got, got_n, got_summary = tc_engine.run_raster(depth, dem, window_method=method)
+    assert got.shape == (h, w) and got_n == n_tiles and got_summary == summary
+    _assert_tc_close(tc_engine, got, want)
