@@ -2,7 +2,7 @@
 
 Nothing under `oracle/` is part of the product: only `tests/`, `__graft_entry__.smoke()` and
 `bench.py`'s CPU-baseline / `--impl reference` legs may import it, and only as the checker.  The product
-package `floodsr_b200` never imports `oracle` (tests/test_layout.py enforces this).
+package `floodsr_b200` never imports `oracle` (tests/test_host_logic.py::test_product_never_imports_the_oracle enforces this).
 
 What restates what (reference paths relative to /root/reference):
 
