@@ -325,6 +325,7 @@ void Engine::setup_windows(int H, int W, int method, int overlap, const int* ys,
   std::vector<int> yf, yc, xf, xc;
   cover(win.ys, Hpad, yf, yc);
   cover(win.xs, Wpad, xf, xc);
+  win.max_cover = std::max(*std::max_element(yc.begin(), yc.end()), *std::max_element(xc.begin(), xc.end()));
   std::vector<int> org((size_t)ny * nx * 2);
   for (int yi = 0; yi < ny; ++yi)
     for (int xi = 0; xi < nx; ++xi) {
@@ -363,6 +364,7 @@ BlendGeom Engine::blend_geom() const {
   g.H = win.H;
   g.W = win.W;
   g.vec_ok = win.vec_ok ? 1 : 0;
+  g.max_cover = win.max_cover;
   return g;
 }
 

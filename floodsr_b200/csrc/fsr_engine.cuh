@@ -19,6 +19,7 @@ struct BlendGeom {
   int T, overlap;
   int H, W;              // cropped output extent
   int vec_ok;            // window x-origins are multiples of 4: float4 path allowed
+  int max_cover;         // largest number of window rows / columns covering one coordinate
 };
 
 
@@ -67,6 +68,7 @@ struct WindowGrid {
   int H = 0, W = 0, T = 0, overlap = 0, method = 0;
   std::vector<int> ys, xs;
   bool vec_ok = true;  // all window x-origins are multiples of 4 pixels
+  int max_cover = 1;   // largest number of window rows / columns covering one coordinate
   DeviceBuf d_ys, d_xs, d_ramp, d_yfirst, d_ycount, d_xfirst, d_xcount, d_origins;
   bool has_ramp = false;
   void release() {

@@ -87,6 +87,93 @@ blend_kernel(const float* __restrict__ tiles, int ty0, int ty1, BlendGeom g, int
   }
 }
 
+// Fast variant for the usual geometry (every pixel is covered by at most 2 window rows and 2 window columns, float4 path):
+// each thread owns 4 pixels of R consecutive rows; the column-side lookups (window indices, feather weights) are done once
+// for all rows, and the up to 4 R tile loads are issued before any is consumed (the kernel is HBM-latency bound).
+// The per-pixel accumulation order is the generic kernel's (window rows outer, columns inner): results are bit-identical.
+template <int R>
+__global__ void __launch_bounds__(256)
+blend_fast_kernel(const float* __restrict__ tiles, int ty0, int ty1, BlendGeom g, int row0, int n_rows,
+                  const float* __restrict__ init, int init_rows, int finalize, float max_depth, float* __restrict__ out) {
+  const int xv = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int rbase = blockIdx.y * R;
+  if (xv >= g.W || rbase >= n_rows) return;
+  const size_t tile_px = (size_t)g.T * g.T;
+  // column side
+  const int xf = g.x_first[xv], xc = g.x_count[xv];
+  int lx[2];
+  float wx[2][4];
+#pragma unroll
+  for (int dx = 0; dx < 2; ++dx) {
+    const int xi = xf + dx;
+    lx[dx] = dx < xc ? xv - g.x_starts[xi] : 0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) wx[dx][v] = (dx < xc && g.ramp) ? edge_weight(g.ramp, lx[dx] + v, xi, g.nx, g.T, g.overlap) : 1.0f;
+  }
+  // row side + loads
+  float4 q[R][2][2];
+  float wy[R][2];
+  bool use[R][2];   // window row contributes to the weight sum
+  bool mine[R][2];  // ... and its tiles belong to this band
+  bool rok[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    rok[r] = rbase + r < n_rows;
+    const int y = row0 + rbase + (rok[r] ? r : 0);
+    const int yf = g.y_first[y], yc = g.y_count[y];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int yi = yf + dy;
+      use[r][dy] = rok[r] && dy < yc;
+      const int ly = use[r][dy] ? y - g.y_starts[yi] : 0;
+      wy[r][dy] = (use[r][dy] && g.ramp) ? edge_weight(g.ramp, ly, yi, g.ny, g.T, g.overlap) : 1.0f;
+      mine[r][dy] = use[r][dy] && yi >= ty0 && yi < ty1;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        q[r][dy][dx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mine[r][dy] && dx < xc)
+          q[r][dy][dx] = __ldcs(reinterpret_cast<const float4*>(tiles + ((size_t)(yi - ty0) * g.nx + xf + dx) * tile_px + (size_t)ly * g.T + lx[dx]));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!rok[r]) continue;
+    const int ry = rbase + r;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (init && ry < init_rows) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(init + (size_t)ry * g.W + xv));
+      acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      if (!use[r][dy]) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        if (dx >= xc) continue;
+        const float p[4] = {q[r][dy][dx].x, q[r][dy][dx].y, q[r][dy][dx].z, q[r][dy][dx].w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float w = __fmul_rn(wy[r][dy], wx[dx][v]);
+          wsum[v] = __fadd_rn(wsum[v], w);
+          if (mine[r][dy]) acc[v] = __fadd_rn(acc[v], __fmul_rn(p[v], w));
+        }
+      }
+    }
+    float o[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (finalize) {
+        const float t = wsum[v] > 0.0f ? __fdiv_rn(acc[v], fmaxf(wsum[v], 1e-6f)) : 0.0f;
+        o[v] = fminf(fmaxf(t, 0.0f), max_depth);
+      } else {
+        o[v] = acc[v];
+      }
+    }
+    *reinterpret_cast<float4*>(out + (size_t)ry * g.W + xv) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace
 
 void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, int row0, int n_rows, const float* d_init,
@@ -100,7 +187,11 @@ void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, in
     const float* init = (d_init && r0 < init_rows) ? d_init + (size_t)r0 * g.W : nullptr;
     const int irows = init ? init_rows - r0 : 0;
     float* outp = d_out + (size_t)r0 * g.W;
-    if (vec) {
+    if (vec && g.max_cover <= 2) {
+      constexpr int R = 2;
+      dim3 grid((unsigned)ceil_div(g.W / 4, 256), (unsigned)ceil_div(nr, R));
+      blend_fast_kernel<R><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp);
+    } else if (vec) {
       dim3 grid((unsigned)ceil_div(g.W / 4, 256), (unsigned)nr);
       blend_kernel<4><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp);
     } else {
