@@ -409,7 +409,7 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   // plus, when dem_lr != nullptr, the scale x scale average pooling of the normalised tile that feeds the network's
   // low-resolution branch (the graph's AveragePool on dem_hr): fixed summation order, no atomics.
   float4* out = reinterpret_cast<float4*>(dem_norm + (size_t)tile_local * T * T);
-  const bool pool = dem_lr != nullptr && scale == 16 && T == 512 && kUnroll == 4;  // thread <-> (row offset t / 128, column vector t % 128)
+  const bool pool = dem_lr != nullptr && scale == 16 && T == 512 && kUnroll % 4 == 0;  // thread <-> (row offset t / 128, column vector t % 128)
   for (int i0 = t; i0 < n_vec; i0 += kThreads * kUnroll) {
     float4 vv[kUnroll];
 #pragma unroll
@@ -418,7 +418,9 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
       int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
       vv[u] = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
     }
-    float psum = 0.0f;
+    float psum[kUnroll / 4];
+#pragma unroll
+    for (int h = 0; h < kUnroll / 4; ++h) psum[h] = 0.0f;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       unsigned dummy = 0;
@@ -430,19 +432,22 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
         e[j] = zero_out ? 0.0f : fminf(fmaxf(n, 0.0f), 1.0f);
       }
       out[i0 + u * kThreads] = make_float4(e[0], e[1], e[2], e[3]);
-      psum += (e[0] + e[1]) + (e[2] + e[3]);
+      psum[u / 4] += (e[0] + e[1]) + (e[2] + e[3]);
     }
     if (pool) {
-      // one outer iteration = kUnroll x 4 = 16 tile rows = one row of pooled cells
-      float q = psum + __shfl_xor_sync(0xffffffffu, psum, 1);
-      q += __shfl_xor_sync(0xffffffffu, q, 2);
-      if ((lane & 3) == 0) pool_part[t >> 7][(t & 127) >> 2] = q;   // [row offset][cell]
-      __syncthreads();
-      if (t < 32) {
-        const float sum = (pool_part[0][t] + pool_part[1][t]) + (pool_part[2][t] + pool_part[3][t]);
-        dem_lr[(size_t)tile_local * (TL * TL) + (i0 / (kThreads * kUnroll)) * TL + t] = sum * (1.0f / 256.0f);
+      // 4 unrolled steps x 4 tile rows = 16 rows = one row of pooled cells
+#pragma unroll
+      for (int h = 0; h < kUnroll / 4; ++h) {
+        float q = psum[h] + __shfl_xor_sync(0xffffffffu, psum[h], 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        if ((lane & 3) == 0) pool_part[t >> 7][(t & 127) >> 2] = q;   // [row offset][cell]
+        __syncthreads();
+        if (t < 32) {
+          const float sum = (pool_part[0][t] + pool_part[1][t]) + (pool_part[2][t] + pool_part[3][t]);
+          dem_lr[(size_t)tile_local * (TL * TL) + ((i0 / (kThreads * kUnroll)) * (kUnroll / 4) + h) * TL + t] = sum * (1.0f / 256.0f);
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   __syncthreads();
