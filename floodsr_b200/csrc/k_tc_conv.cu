@@ -231,26 +231,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
 
 // ---- persistent row-box variant for the wide, shallow levels ------------------------------------------------------
-// For 3x3 layers whose M tile (128 pixels = bh whole image rows of width bw == W) lies inside one image and whose
-// packed weights fit in shared memory.  One CTA per SM loops over M tiles:
+// For 3x3 layers on 32- and 16-pixel-wide maps whose packed weights fit in shared memory.  One CTA per SM loops over M tiles:
 //   * the weights are loaded once per CTA;
-//   * per (M tile, 32-channel group) only THREE halo boxes are fetched (dx = -1, 0, +1; bh + 2 rows each): the dy taps
-//     are row offsets (bw * 16 B) into a box, so the L2 -> shared-memory traffic is 3 boxes instead of 9;
+//   * pixels are enumerated in a PADDED pitch (image width + 8): an M tile is 128 consecutive positions of that
+//     enumeration, and ONE halo box (pitch pixels wide starting at x = -1, all rows the tile touches + 1 above / below) is
+//     fetched per (M tile, 32-channel group).  Because the box rows are `pitch` pixels apart in shared memory too, tap
+//     (ky, kx) of every position is the box shifted by (ky * pitch + kx) * 16 bytes: nine taps from one fetch instead of
+//     nine (or three) fetches.  The price is 25 % (W = 32) / 50 % (W = 16) of positions that are padding and are dropped
+//     in the epilogue; the kernel is fetch-bound, not MMA-bound (N <= 64);
 //   * accumulators are double-buffered in TMEM, so the epilogue of tile t overlaps the MMAs of tile t + 1, and the
 //     per-CTA set-up (TMEM allocation, barrier init, first TMA latency) is paid once per SM instead of once per tile.
-constexpr int kRowMaxStages = 6;
+constexpr int kRowMaxStages = 8;
 
 struct ConvRowsParams {
   int H, W, N;
-  int bw, bh;          // bw == W, bw * bh == 128
-  int tiles_per_img;   // H / bh
+  int pitch;           // W + 8
+  int box_rows;        // rows of the halo box (rows an M tile can touch + 2)
+  int tiles_per_img;   // H * pitch / 128
   int n_mtiles;        // N * tiles_per_img
   int kc;              // 8-channel planes per channel group (2 or 4)
   int g0, g1;          // channel groups coming from src0 / src1
   int cout, act;
   float alpha;
   int half;
-  int stages;          // halo-box ring depth (as many as fit beside the weights: the kernel is fetch-latency bound)
+  int stages;          // halo-box ring depth (as many as fit beside the weights)
   long long plane;     // pixels per CP8 plane of the output/residual tensors
   const __nv_bfloat16* wpack;  // [tap][group][kc][BN][8]
   int w_bytes;
@@ -263,16 +267,17 @@ template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int plane_b = (p.bh + 2) * p.bw * 16;       // one 8-channel plane of a halo box
-  const int dx_bytes = p.kc * plane_b;               // one box
+  const int plane_b = p.box_rows * p.pitch * 16;    // one 8-channel plane of a halo box
+  const int box_bytes = p.kc * plane_b;
+  const int stage_bytes = (box_bytes + 2 * p.pitch * 16 + 127) & ~127;  // slack: the last taps of padding positions read past the box
   const int w_round = (p.w_bytes + 1023) & ~1023;
   uint8_t* smem_w = smem_raw;
-  uint8_t* smem_a = smem_raw + w_round;              // p.stages x 3 boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * 3 * dx_bytes);
+  uint8_t* smem_a = smem_raw + w_round;              // p.stages boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * stage_bytes);
   uint64_t* w_full = bars;
   uint64_t* full = bars + 1;                 // [p.stages]
-  uint64_t* empty = full + p.stages;       // [p.stages]
-  uint64_t* acc_full = empty + p.stages;   // [2]
+  uint64_t* empty = full + p.stages;         // [p.stages]
+  uint64_t* acc_full = empty + p.stages;     // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -300,6 +305,9 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
+  // the slack behind every box is only ever multiplied into discarded padding positions, but must not hold NaN/Inf patterns
+  for (int i = threadIdx.x; i < p.stages * stage_bytes / 16; i += kConvThreads) reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -310,18 +318,19 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (lane == 0) {
       mbar_expect_tx(w_full, (uint32_t)p.w_bytes);
       bulk_load_1d(smem_w, p.wpack, (uint32_t)p.w_bytes, w_full);
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 1;
       for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
-        const int img = mt / p.tiles_per_img, ty = mt % p.tiles_per_img;
-        for (int g = 0; g < groups; ++g, ++it) {
-          const int s = it % p.stages;
-          mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
-          mbar_expect_tx(&full[s], 3u * (uint32_t)dx_bytes);
+        const int img = mt / p.tiles_per_img, t = mt % p.tiles_per_img;
+        const int r0 = (t * 128) / p.pitch;  // image row of the tile's first position
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&empty[s], ph);
+          mbar_expect_tx(&full[s], (uint32_t)box_bytes);
           const bool second = g >= p.g0;
           const CUtensorMap* tm = second ? &tmA1 : &tmA0;
           const int chunk0 = (second ? g - p.g0 : g) * p.kc;
-          for (int dxi = 0; dxi < 3; ++dxi)
-            tma_load_5d(smem_a + (s * 3 + dxi) * dx_bytes, tm, &full[s], 0, dxi - 1, ty * p.bh - 1, img, chunk0);
+          tma_load_5d(smem_a + s * stage_bytes, tm, &full[s], 0, -1, r0 - 1, img, chunk0);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -331,8 +340,8 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     mbar_wait(w_full, 0);
     const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a), (uint32_t)plane_b);
     const uint32_t b_lo0 = desc_lo32(smem_u32(smem_w), BN * 16);
-    const uint32_t dx_u = (uint32_t)dx_bytes >> 4, row_u = (uint32_t)p.bw;      // box / image-row strides in 16-byte units
-    const uint32_t kpl_u = (uint32_t)(2 * plane_b) >> 4;                          // one MMA = two channel planes
+    const uint32_t st_u = (uint32_t)stage_bytes >> 4, row_u = (uint32_t)p.pitch;  // stage / image-row strides in 16-byte units
+    const uint32_t kpl_u = (uint32_t)(2 * plane_b) >> 4;                            // one MMA = two channel planes
     const uint32_t wtap_u = (uint32_t)(groups * p.kc * BN * 16) >> 4, wgrp_u = (uint32_t)(p.kc * BN * 16) >> 4;
     const int kpairs = p.kc / 2;
     const bool leader = elect_one();
@@ -340,17 +349,19 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint32_t ph = 0;
     for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++nt) {
       const int ab = nt & 1;
+      const int t = mt % p.tiles_per_img;
+      const uint32_t c0 = (uint32_t)((t * 128) % p.pitch);  // column (in the padded pitch) of the tile's first position
       mbar_wait(&acc_empty[ab], ((nt >> 1) & 1) ^ 1);
       const uint32_t d = tmem_base + ab * BN;
       for (int g = 0; g < groups; ++g) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (leader) {
-          const uint32_t a_s = a_lo0 + (uint32_t)s * 3 * dx_u;
+          const uint32_t a_s = a_lo0 + (uint32_t)s * st_u + c0;
           const uint32_t b_g = b_lo0 + (uint32_t)g * wgrp_u;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_t = a_s + (tap % 3) * dx_u + (tap / 3) * row_u;
+            const uint32_t a_t = a_s + (tap / 3) * row_u + (tap % 3);
             const uint32_t b_t = b_g + tap * wtap_u;
             umma_lo(d, a_t, b_t, kDescHi, idesc, (g > 0 || tap > 0) ? 1u : 0u);
             if (kpairs > 1) umma_lo(d, a_t + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
@@ -366,14 +377,16 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int lx = m % p.bw, ly = m / p.bw;
     int nt = 0;
     for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++nt) {
       const int ab = nt & 1;
-      const int img = mt / p.tiles_per_img, ty = mt % p.tiles_per_img;
-      const long long pix = ((long long)img * p.H + (ty * p.bh + ly)) * p.W + lx;
+      const int img = mt / p.tiles_per_img, t = mt % p.tiles_per_img;
+      const int pos = t * 128 + m;
+      const int y = pos / p.pitch, x = pos - y * p.pitch;
+      const bool valid = x < p.W && y < p.H;   // padding positions are dropped
+      const long long pix = ((long long)img * p.H + y) * p.W + x;
       uint4 resv[BN / 8];  // fetched while the tile's MMAs still run
-      if (p.res) {
+      if (p.res && valid) {
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)c * p.plane + pix) * 8));
       }
@@ -385,28 +398,30 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         float v[32];
         tmem_ld32(taddr + c32 * 32, v);
         tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int co = c32 * 32 + c * 8;
-          const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
-          float o[8];
+          for (int c = 0; c < 4; ++c) {
+            const int co = c32 * 32 + c * 8;
+            const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
+            float o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = v[c * 8 + i];
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
-            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-            o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            for (int i = 0; i < 8; ++i) o[i] = v[c * 8 + i];
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (p.res) {
+              float r[8];
+              unpack_x8(resv[c32 * 4 + c], r, p.half);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] += r[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = apply_act(o[i], p.act, p.alpha);
+            *reinterpret_cast<uint4*>(p.out + off) = pack_x8(o, p.half);
           }
-          if (p.res) {
-            float r[8];
-            unpack_x8(resv[c32 * 4 + c], r, p.half);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += r[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = apply_act(o[i], p.act, p.alpha);
-          *reinterpret_cast<uint4*>(p.out + off) = pack_x8(o, p.half);
         }
       }
       tc_fence_before();
@@ -722,14 +737,28 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
 }
 
 
-// Row-box variant: usable when an M tile is bh whole rows of one image and the packed weights fit in shared memory.
+// Row-box variant: 32- or 16-pixel-wide maps whose padded enumeration tiles into whole 128-position M tiles and whose packed
+// weights fit in shared memory.
+static void conv_rows_geometry(int H, int W, int& pitch, int& box_rows, int& tiles_per_img) {
+  pitch = W + 8;
+  tiles_per_img = H * pitch / 128;
+  int span = 1;  // image rows one M tile can touch
+  for (int t = 0; t < tiles_per_img; ++t) span = std::max(span, (t * 128 + 127) / pitch - (t * 128) / pitch + 1);
+  box_rows = span + 2;
+}
+
+static size_t conv_rows_stage_bytes(int kc, int box_rows, int pitch) {
+  return ((size_t)kc * box_rows * pitch * 16 + 2 * pitch * 16 + 127) & ~(size_t)127;
+}
+
 bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc) {
   if (ksz != 3 || (W != 16 && W != 32) || (cout != 32 && cout != 64)) return false;
-  const int bh = 128 / W;
-  if (H % bh) return false;
+  if ((H * (W + 8)) % 128) return false;
   if (kc != 2 && kc != 4) return false;
+  int pitch, box_rows, tiles_per_img;
+  conv_rows_geometry(H, W, pitch, box_rows, tiles_per_img);
   const size_t w_bytes = (size_t)9 * ((C0 + C1) / 8) * cout * 16;
-  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + (size_t)3 * 3 * kc * (bh + 2) * W * 16 + 256;  // >= 3 stages
+  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + 3 * conv_rows_stage_bytes(kc, box_rows, pitch) + 256;  // >= 3 stages
   return smem <= 200 * 1024;
 }
 
@@ -739,8 +768,7 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
                          cudaStream_t s) {
   ConvRowsParams p{};
   p.H = H; p.W = W; p.N = n_img;
-  p.bw = W; p.bh = 128 / W;
-  p.tiles_per_img = H / p.bh;
+  conv_rows_geometry(H, W, p.pitch, p.box_rows, p.tiles_per_img);
   p.n_mtiles = n_img * p.tiles_per_img;
   p.kc = kc;
   p.g0 = (C0 / 8) / kc;
@@ -750,9 +778,9 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   p.wpack = wpack;
   p.w_bytes = 9 * (p.g0 + p.g1) * kc * cout * 16;
   p.bias = bias; p.res = res; p.out = dst;
-  CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh + 2, 1, kc);
-  CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh + 2, 1, kc) : m0;
-  const size_t w_round = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023), stage_bytes = (size_t)3 * kc * (p.bh + 2) * W * 16;
+  CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.pitch, p.box_rows, 1, kc);
+  CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.pitch, p.box_rows, 1, kc) : m0;
+  const size_t w_round = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023), stage_bytes = conv_rows_stage_bytes(kc, p.box_rows, p.pitch);
   p.stages = (int)std::min<size_t>(kRowMaxStages, (200 * 1024 - 256 - w_round) / stage_bytes);
   const size_t smem = w_round + (size_t)p.stages * stage_bytes + 256;
   const int grid = p.n_mtiles < n_sms ? p.n_mtiles : n_sms;
