@@ -140,8 +140,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const bool second = st >= p.s0;
           const CUtensorMap* tm = second ? &tmA1 : &tmA0;
           const int chunk0 = (second ? st - p.s0 : st) * p.kc;
-          if (p.im) tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 0, tn * 128, (ty + dy) * p.W + tx + dx, 0, chunk0);
-          else tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 0, tx * p.bw + dx, ty * p.bh + dy, tn * p.bn, chunk0);
+          if (p.im) tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], tn * 256, (ty + dy) * p.W + tx + dx, chunk0, 0, 0);
+          else tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 2 * (tx * p.bw + dx), ty * p.bh + dy, tn * p.bn, chunk0, 0);
           const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)p.kc * BN * 8);
           bulk_load_1d(smem_b + s * kBBytesMax, wsrc, b_bytes, &full[s]);
         }
@@ -329,7 +329,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           const bool second = g >= p.g0;
           const CUtensorMap* tm = second ? &tmA1 : &tmA0;
           const int chunk0 = (second ? g - p.g0 : g) * p.kc;
-          tma_load_5d(smem_a + s * stage_bytes, tm, &full[s], 0, -1, r0 - 1, img, chunk0);
+          tma_load_5d(smem_a + s * stage_bytes, tm, &full[s], -2, r0 - 1, img, chunk0, 0);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -639,18 +639,36 @@ CUtensorMap make_cp8_tensor_map(const void* base, int W, int H, int N, int chunk
   return m;
 }
 
-// 5-D tensor map over an IM8 activation tensor [C/8][H*W][ncap][8]: dims (8, ncap, H*W, 1, C/8); box (8, 128, 1, 1, kc) =
-// 128 images at one pixel, kc channel chunks: every chunk is one contiguous 2 KB run.
+// The same CP8 tensor with the 8-channel vector and the x axis described as ONE inner dimension of 64-bit elements (two per
+// pixel): dims (2W, H, N, C/8, 1); box (2 bw, bh, bn, kc, 1); x coordinates are doubled.  The TMA unit works row by row of the
+// innermost dimension, so a box row is bw * 16 bytes instead of 16: a 40-pixel halo box is 24 requests instead of 960.
+CUtensorMap make_cp8_wide_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc) {
+  CUtensorMap m;
+  cuuint64_t dims[5] = {(cuuint64_t)2 * W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)chunks, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)plane * 16, (cuuint64_t)plane * 16 * chunks};
+  cuuint32_t box[5] = {(cuuint32_t)2 * bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)kc, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (2 * bw > 256) throw Error(FSR_E_INVALID, "wide CP8 box exceeds 256 elements");
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(FSR_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+// 5-D tensor map over an IM8 activation tensor [C/8][H*W][ncap][8], in 64-bit elements: dims (2 ncap, H*W, C/8, 1, 1);
+// box (256, 1, kc, 1, 1) = 128 images at one pixel, kc channel chunks: every chunk is one contiguous 2 KB row.
 CUtensorMap make_im8_tensor_map(const void* base, long long ncap, int HW, int chunks, int kc) {
   CUtensorMap m;
-  cuuint64_t dims[5] = {8, (cuuint64_t)ncap, (cuuint64_t)HW, 1, (cuuint64_t)chunks};
-  cuuint64_t strides[4] = {16, (cuuint64_t)ncap * 16, (cuuint64_t)HW * ncap * 16, (cuuint64_t)HW * ncap * 16};
-  cuuint32_t box[5] = {8, 128, 1, 1, (cuuint32_t)kc};
+  cuuint64_t dims[5] = {(cuuint64_t)2 * ncap, (cuuint64_t)HW, (cuuint64_t)chunks, 1, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)ncap * 16, (cuuint64_t)HW * ncap * 16, (cuuint64_t)HW * ncap * 16 * chunks,
+                           (cuuint64_t)HW * ncap * 16 * chunks};
+  cuuint32_t box[5] = {256, 1, (cuuint32_t)kc, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw Error(FSR_E_CUDA, "cuTensorMapEncodeTiled (IM8) failed with code " + std::to_string((int)r));
+  if (r != CUDA_SUCCESS) throw Error(FSR_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return m;
 }
 
@@ -710,10 +728,10 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   p.out = dst;
   const int tiles_n = ceil_div(n_img, p.bn);
   CUtensorMap m0 = im ? make_im8_tensor_map(src0, plane0 / ((long long)H * W), H * W, C0 / 8, kc)
-                      : make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc);
+                      : make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc);
   CUtensorMap m1 = !src1 ? m0
                    : im  ? make_im8_tensor_map(src1, plane1 / ((long long)H * W), H * W, C1 / 8, kc)
-                         : make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc);
+                         : make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc);
   const int BN = conv_tc_bn(cout);
   const int n_iters = ksz * ksz * (p.s0 + p.s1);
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)ceil_div(cout, BN));
@@ -778,8 +796,8 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   p.wpack = wpack;
   p.w_bytes = 9 * (p.g0 + p.g1) * kc * cout * 16;
   p.bias = bias; p.res = res; p.out = dst;
-  CUtensorMap m0 = make_cp8_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.pitch, p.box_rows, 1, kc);
-  CUtensorMap m1 = src1 ? make_cp8_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.pitch, p.box_rows, 1, kc) : m0;
+  CUtensorMap m0 = make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.pitch, p.box_rows, 1, kc);
+  CUtensorMap m1 = src1 ? make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.pitch, p.box_rows, 1, kc) : m0;
   const size_t w_round = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023), stage_bytes = conv_rows_stage_bytes(kc, p.box_rows, p.pitch);
   p.stages = (int)std::min<size_t>(kRowMaxStages, (200 * 1024 - 256 - w_round) / stage_bytes);
   const size_t smem = w_round + (size_t)p.stages * stage_bytes + 256;

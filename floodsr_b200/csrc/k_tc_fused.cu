@@ -34,7 +34,7 @@ namespace fsr {
 
 using namespace tc;
 
-CUtensorMap make_cp8_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc);
+CUtensorMap make_cp8_wide_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc);
 
 namespace {
 
@@ -244,7 +244,7 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
             mbar_expect_tx(&wt_full[st], kWtStage);
             uint8_t* dst = smem_wt + st * kWtStage;
             bulk_load_1d(dst, reinterpret_cast<const uint8_t*>(p.wt) + (size_t)(y & (kUp - 1)) * kWtRow + h * kWtHalf, kWtHalf, &wt_full[st]);
-            tma_load_5d(dst + kWtHalf, &tmL, &wt_full[st], 0, 0, y / kUp, it.img, 0);
+            tma_load_5d(dst + kWtHalf, &tmL, &wt_full[st], 0, y / kUp, it.img, 0, 0);
             if (++st == kWtStages) { st = 0; ph ^= 1; }
           }
         }
@@ -584,7 +584,7 @@ void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_
   }
   p.b2 = b2 ? b2[0] : 0.0f;
   // L as TMA source: one LR row of 32 cells, all 4 channel planes -> [4 planes][32 cells][8] (the convT B operand)
-  CUtensorMap mL = make_cp8_tensor_map(lr, kCells, H / kUp, n_img, 4, lr_plane, kCells, 1, 1, 4);
+  CUtensorMap mL = make_cp8_wide_tensor_map(lr, kCells, H / kUp, n_img, 4, lr_plane, kCells, 1, 1, 4);
   const int grid = p.total_rows < n_sms ? (int)p.total_rows : n_sms;
   auto go = [&](auto kernel) {
     FSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
