@@ -188,7 +188,7 @@ class Engine {
   int cap_tiles_ = 0;            // arena capacity (tiles per chunk)
   int hr_sub_ = 4;               // tiles per HR sub-chunk (tensor-core modes: 64; env FSR_HR_SUB overrides)
   int chunk_tiles_ = 64;
-  int band_tiles_ = 192;         // windows per band of the fsr_run_raster copy/compute pipeline (env FSR_BAND_TILES)
+  int band_tiles_ = 170;         // windows per band of the fsr_run_raster copy/compute pipeline (env FSR_BAND_TILES)
   DeviceBuf d_weights_, d_flags_, d_headmid_;
   std::vector<DeviceBuf> tbuf_;
   std::vector<float*> tbase_;    // per-forward tensor base pointers (inputs/outputs alias caller buffers)

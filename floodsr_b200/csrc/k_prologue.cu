@@ -32,11 +32,16 @@ struct SelState {
   int rank;         // rank of the wanted element among keys in [lo, hi]
 };
 
-__device__ __forceinline__ float fix_dem(float x, const fsr_tile_params& p, unsigned& flags) {
+__device__ __forceinline__ float fix_nodata(float x, const fsr_tile_params& p) {
   if (p.has_dem_nodata) {
     bool hit = (x == p.dem_nodata) || (p.dem_nodata_tol >= 0.0f && fabsf(x - p.dem_nodata) <= p.dem_nodata_tol);
     if (hit) x = 0.0f;
   }
+  return x;
+}
+
+__device__ __forceinline__ float fix_dem(float x, const fsr_tile_params& p, unsigned& flags) {
+  x = fix_nodata(x, p);
   if (!isfinite(x)) {
     flags |= FSR_FLAG_DEM_NONFINITE;
     x = 0.0f;
@@ -180,6 +185,24 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   const int2 org = grid.origins[tile_base + tile_local];
   const int vec_per_row = T / 4;
   const int n_vec = T * vec_per_row;
+  // tile-uniform fast addressing: power-of-two rows split with a shift, and windows that lie wholly inside the raster on
+  // 16-byte boundaries skip the per-vector bounds and alignment tests
+  const int vsh = (vec_per_row & (vec_per_row - 1)) == 0 ? __ffs(vec_per_row) - 1 : -1;
+  const bool interior = org.x + T <= grid.H && org.y + T <= grid.W && (grid.W & 3) == 0 && (org.y & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(dem) & 15u) == 0;
+  const float* tile0 = dem + (size_t)org.x * (size_t)grid.W + (size_t)org.y;
+  auto tile_load4 = [&](int i) {
+    int r, c;
+    if (vsh >= 0) {
+      r = i >> vsh;
+      c = (i & (vec_per_row - 1)) * 4;
+    } else {
+      r = i / vec_per_row;
+      c = (i - r * vec_per_row) * 4;
+    }
+    if (interior) return __ldg(reinterpret_cast<const float4*>(tile0 + (size_t)r * (size_t)grid.W + c));
+    return load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+  };
   const int n_px = T * T;
   unsigned my_flags = 0;
   if (t == 0) {
@@ -271,9 +294,7 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
     float4 vv[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = i0 + u * kThreads;
-      int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-      vv[u] = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+      vv[u] = tile_load4(i0 + u * kThreads);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -366,8 +387,7 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
       }
     } else {
       for (int i = t; i < n_vec; i += kThreads) {
-        int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-        float4 v = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+        float4 v = tile_load4(i);
         unsigned dummy = 0;
         float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -414,20 +434,18 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
     float4 vv[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = i0 + u * kThreads;
-      int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
-      vv[u] = load4(dem, grid.H, grid.W, org.x + r, org.y + c);
+      vv[u] = tile_load4(i0 + u * kThreads);
     }
     float psum[kUnroll / 4];
 #pragma unroll
     for (int h = 0; h < kUnroll / 4; ++h) psum[h] = 0.0f;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      unsigned dummy = 0;
       float e[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float x = fminf(fmaxf(fix_dem(e[j], p, dummy), 0.0f), p_clip);
+        // non-finite values were flagged in pass A (the call fails); fmaxf / fminf map NaN to 0 and +-Inf into the clip range
+        float x = fminf(fmaxf(fix_nodata(e[j], p), 0.0f), p_clip);
         float n = __fdiv_rn(__fsub_rn(x, dem_min), range_f);
         e[j] = zero_out ? 0.0f : fminf(fmaxf(n, 0.0f), 1.0f);
       }
