@@ -242,10 +242,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 //   * accumulators are double-buffered in TMEM, so the epilogue of tile t overlaps the MMAs of tile t + 1, and the
 //     per-CTA set-up (TMEM allocation, barrier init, first TMA latency) is paid once per SM instead of once per tile.
 constexpr int kRowMaxStages = 8;
+constexpr int kRowsEpiSets = 4;                       // epilogue warp sets (one per accumulator buffer)
+constexpr int kRowsIssuers = 2;                       // MMA-issuing warps (tiles dealt round-robin)
+constexpr int kRowsThreads = 32 + 32 * kRowsIssuers + 128 * kRowsEpiSets;  // producer warp, MMA warps, one epilogue set per accumulator buffer
+template <int BN>
+constexpr int kRowsTmemCols = kRowsEpiSets * BN <= 64 ? 64 : kRowsEpiSets * BN <= 128 ? 128 : kRowsEpiSets * BN <= 256 ? 256 : 512;
 
 struct ConvRowsParams {
   int H, W, N;
   int pitch;           // W + 8
+  unsigned pitch_magic;  // ceil(2^32 / pitch): position / pitch as a multiply-high
   int box_rows;        // rows of the halo box (rows an M tile can touch + 2)
   int tiles_per_img;   // H * pitch / 128
   int n_mtiles;        // N * tiles_per_img
@@ -255,6 +261,7 @@ struct ConvRowsParams {
   float alpha;
   int half;
   int stages;          // halo-box ring depth (as many as fit beside the weights)
+  unsigned long long* stats;  // FSR_ROWS_STATS: per-CTA clock totals of the pipeline roles (diagnostics)
   long long plane;     // pixels per CP8 plane of the output/residual tensors
   const __nv_bfloat16* wpack;  // [tap][group][kc][BN][8]
   int w_bytes;
@@ -264,7 +271,7 @@ struct ConvRowsParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int plane_b = p.box_rows * p.pitch * 16;    // one 8-channel plane of a halo box
@@ -277,9 +284,10 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* w_full = bars;
   uint64_t* full = bars + 1;                 // [p.stages]
   uint64_t* empty = full + p.stages;         // [p.stages]
-  uint64_t* acc_full = empty + p.stages;     // [2]
-  uint64_t* acc_empty = acc_full + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = empty + p.stages;                // [kRowsEpiSets]
+  uint64_t* acc_empty = acc_full + kRowsEpiSets;        // [kRowsEpiSets]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kRowsEpiSets);
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = p.g0 + p.g1;
@@ -295,18 +303,19 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < kRowsEpiSets; ++i) {
         mbar_init(&acc_full[i], 1);
         mbar_init(&acc_empty[i], 4);
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, kRowsTmemCols<BN>);
     tmem_relinquish();
   }
+  if (threadIdx.x < BN) s_bias[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.0f;
   // the slack behind every box is only ever multiplied into discarded padding positions, but must not hold NaN/Inf patterns
-  for (int i = threadIdx.x; i < p.stages * stage_bytes / 16; i += kConvThreads) reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < p.stages * stage_bytes / 16; i += kRowsThreads) reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -320,11 +329,16 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       bulk_load_1d(smem_w, p.wpack, (uint32_t)p.w_bytes, w_full);
       int s = 0;
       uint32_t ph = 1;
+      long long st_wait = 0;
+      const long long c_start = p.stats ? clock64() : 0;
+      int img = (int)(blockIdx.x / p.tiles_per_img), t = (int)(blockIdx.x % p.tiles_per_img);
+      const int step_img = (int)(gridDim.x / p.tiles_per_img), step_t = (int)(gridDim.x % p.tiles_per_img);
       for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
-        const int img = mt / p.tiles_per_img, t = mt % p.tiles_per_img;
-        const int r0 = (t * 128) / p.pitch;  // image row of the tile's first position
+        const int r0 = (int)__umulhi((unsigned)(t * 128), p.pitch_magic);  // image row of the tile's first position
         for (int g = 0; g < groups; ++g) {
+          const long long c_a = p.stats ? clock64() : 0;
           mbar_wait(&empty[s], ph);
+          if (p.stats) st_wait += clock64() - c_a;
           mbar_expect_tx(&full[s], (uint32_t)box_bytes);
           const bool second = g >= p.g0;
           const CUtensorMap* tm = second ? &tmA1 : &tmA0;
@@ -332,10 +346,20 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           tma_load_5d(smem_a + s * stage_bytes, tm, &full[s], -2, r0 - 1, img, chunk0, 0);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        t += step_t;
+        img += step_img;
+        if (t >= p.tiles_per_img) { t -= p.tiles_per_img; ++img; }
+      }
+      if (p.stats) {
+        p.stats[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - c_start);
+        p.stats[blockIdx.x * 16 + 1] = (unsigned long long)st_wait;
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp <= kRowsIssuers) {
+    // ===================== MMA issuers: warp 1 + e takes tiles e, e + kRowsIssuers, ...; tile nt uses accumulator buffer nt % kRowsEpiSets =====================
+    // One thread issues an N <= 64 MMA more slowly than the tensor pipe retires it (descriptor arithmetic + issue latency),
+    // so the tiles are dealt to kRowsIssuers issuing warps whose MMAs interleave in the pipe.
+    const int e = warp - 1;
     const uint32_t idesc = idesc_16(128, BN, p.half);
     mbar_wait(w_full, 0);
     const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a), (uint32_t)plane_b);
@@ -345,16 +369,25 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t wtap_u = (uint32_t)(groups * p.kc * BN * 16) >> 4, wgrp_u = (uint32_t)(p.kc * BN * 16) >> 4;
     const int kpairs = p.kc / 2;
     const bool leader = elect_one();
-    int s = 0, nt = 0;
+    int nt = e;
+    long long w_acc = 0, w_full = 0, n_t = 0;
+    const long long c_start = p.stats ? clock64() : 0;
+    int t = (int)((blockIdx.x + e * gridDim.x) % p.tiles_per_img);
+    const int step_t = (int)((kRowsIssuers * gridDim.x) % p.tiles_per_img);
+    int s = e * groups;
     uint32_t ph = 0;
-    for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++nt) {
-      const int ab = nt & 1;
-      const int t = mt % p.tiles_per_img;
-      const uint32_t c0 = (uint32_t)((t * 128) % p.pitch);  // column (in the padded pitch) of the tile's first position
-      mbar_wait(&acc_empty[ab], ((nt >> 1) & 1) ^ 1);
+    while (s >= p.stages) { s -= p.stages; ph ^= 1; }
+    for (int mt = blockIdx.x + e * gridDim.x; mt < p.n_mtiles; mt += kRowsIssuers * gridDim.x, nt += kRowsIssuers) {
+      const int ab = nt % kRowsEpiSets;
       const uint32_t d = tmem_base + ab * BN;
+      const uint32_t c0 = (uint32_t)(t * 128) - __umulhi((unsigned)(t * 128), p.pitch_magic) * (uint32_t)p.pitch;  // column (in the padded pitch) of the tile's first position
+      long long c_a = p.stats ? clock64() : 0;
+      mbar_wait(&acc_empty[ab], ((nt / kRowsEpiSets) & 1) ^ 1);
+      if (p.stats) { w_acc += clock64() - c_a; ++n_t; }
       for (int g = 0; g < groups; ++g) {
+        c_a = p.stats ? clock64() : 0;
         mbar_wait(&full[s], ph);
+        if (p.stats) w_full += clock64() - c_a;
         tc_fence_after();
         if (leader) {
           const uint32_t a_s = a_lo0 + (uint32_t)s * st_u + c0;
@@ -372,17 +405,36 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      // the other issuers' boxes of the ring (shared by all issuers, filled in tile order)
+      s += (kRowsIssuers - 1) * groups;
+      while (s >= p.stages) { s -= p.stages; ph ^= 1; }
+      t += step_t;
+      if (t >= p.tiles_per_img) t -= p.tiles_per_img;
+    }
+    if (p.stats && lane == 0) {
+      p.stats[blockIdx.x * 16 + 2 + e * 4] = (unsigned long long)(clock64() - c_start);
+      p.stats[blockIdx.x * 16 + 3 + e * 4] = (unsigned long long)w_acc;
+      p.stats[blockIdx.x * 16 + 4 + e * 4] = (unsigned long long)w_full;
+      p.stats[blockIdx.x * 16 + 5 + e * 4] = (unsigned long long)n_t;
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue: kRowsEpiSets sets of 4 warps, set e drains accumulator buffer e =====================
+    // One warp retires a dependent instruction every few cycles, so a single set of four warps (one per TMEM lane
+    // quarter) needs longer per tile than the tile's MMAs; two sets work on alternate tiles.
+    const int set = (warp - 1 - kRowsIssuers) >> 2;
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    int nt = 0;
-    for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++nt) {
-      const int ab = nt & 1;
-      const int img = mt / p.tiles_per_img, t = mt % p.tiles_per_img;
+    // (image, tile-in-image) advance without divisions
+    const int first = blockIdx.x + set * gridDim.x, step = kRowsEpiSets * gridDim.x;
+    int img = first / p.tiles_per_img, t = first % p.tiles_per_img;
+    const int step_img = step / p.tiles_per_img, step_t = step % p.tiles_per_img;
+    int nt = set;
+    long long e_wait = 0, e_ld = 0;
+    const long long e_start = p.stats ? clock64() : 0;
+    for (int mt = first; mt < p.n_mtiles; mt += step, nt += kRowsEpiSets) {
+      const int ab = set;
       const int pos = t * 128 + m;
-      const int y = pos / p.pitch, x = pos - y * p.pitch;
+      const int y = (int)__umulhi((unsigned)pos, p.pitch_magic), x = pos - y * p.pitch;
       const bool valid = x < p.W && y < p.H;   // padding positions are dropped
       const long long pix = ((long long)img * p.H + y) * p.W + x;
       uint4 resv[BN / 8];  // fetched while the tile's MMAs still run
@@ -390,7 +442,9 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)c * p.plane + pix) * 8));
       }
-      mbar_wait(&acc_full[ab], (nt >> 1) & 1);
+      const long long c_a = p.stats ? clock64() : 0;
+      mbar_wait(&acc_full[ab], (nt / kRowsEpiSets) & 1);
+      if (p.stats) e_wait += clock64() - c_a;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN;
 #pragma unroll
@@ -398,19 +452,23 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         float v[32];
         tmem_ld32(taddr + c32 * 32, v);
         tmem_ld_wait();
+        if (c32 == BN / 32 - 1) {
+          // the accumulator is in registers: hand the buffer back before the arithmetic and the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          if (p.stats) e_ld += clock64() - c_a;
+        }
         if (valid) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int co = c32 * 32 + c * 8;
             const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
             float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = v[c * 8 + i];
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
-              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co), b1 = *reinterpret_cast<const float4*>(s_bias + co + 4);
+              o[0] = v[c * 8] + b0.x; o[1] = v[c * 8 + 1] + b0.y; o[2] = v[c * 8 + 2] + b0.z; o[3] = v[c * 8 + 3] + b0.w;
+              o[4] = v[c * 8 + 4] + b1.x; o[5] = v[c * 8 + 5] + b1.y; o[6] = v[c * 8 + 6] + b1.z; o[7] = v[c * 8 + 7] + b1.w;
             }
             if (p.res) {
               float r[8];
@@ -418,21 +476,31 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] += r[i];
             }
+            if (p.act == FSR_ACT_RELU) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = apply_act(o[i], p.act, p.alpha);
+              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.0f);
+            } else if (p.act == FSR_ACT_LEAKY) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.0f ? o[i] : o[i] * p.alpha;
+            }
             *reinterpret_cast<uint4*>(p.out + off) = pack_x8(o, p.half);
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      t += step_t;
+      img += step_img;
+      if (t >= p.tiles_per_img) { t -= p.tiles_per_img; ++img; }
+    }
+    if (p.stats && set == 0 && q == 0 && lane == 0) {
+      p.stats[blockIdx.x * 16 + 10] = (unsigned long long)(clock64() - e_start);
+      p.stats[blockIdx.x * 16 + 11] = (unsigned long long)e_wait;
+      p.stats[blockIdx.x * 16 + 12] = (unsigned long long)e_ld;
     }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, kRowsTmemCols<BN>);
   }
 }
 
@@ -776,7 +844,7 @@ bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc) {
   int pitch, box_rows, tiles_per_img;
   conv_rows_geometry(H, W, pitch, box_rows, tiles_per_img);
   const size_t w_bytes = (size_t)9 * ((C0 + C1) / 8) * cout * 16;
-  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + 3 * conv_rows_stage_bytes(kc, box_rows, pitch) + 256;  // >= 3 stages
+  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + 3 * conv_rows_stage_bytes(kc, box_rows, pitch) + 512;  // >= 3 stages
   return smem <= 200 * 1024;
 }
 
@@ -787,6 +855,10 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   ConvRowsParams p{};
   p.H = H; p.W = W; p.N = n_img;
   conv_rows_geometry(H, W, p.pitch, p.box_rows, p.tiles_per_img);
+  p.pitch_magic = (unsigned)((0x100000000ull + p.pitch - 1) / p.pitch);
+  static unsigned long long* d_stats = nullptr;
+  if (getenv("FSR_ROWS_STATS") && !d_stats) FSR_CUDA(cudaMalloc(&d_stats, 148 * 16 * sizeof(unsigned long long)));
+  p.stats = d_stats;
   p.n_mtiles = n_img * p.tiles_per_img;
   p.kc = kc;
   p.g0 = (C0 / 8) / kc;
@@ -799,17 +871,25 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   CUtensorMap m0 = make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.pitch, p.box_rows, 1, kc);
   CUtensorMap m1 = src1 ? make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.pitch, p.box_rows, 1, kc) : m0;
   const size_t w_round = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023), stage_bytes = conv_rows_stage_bytes(kc, p.box_rows, p.pitch);
-  p.stages = (int)std::min<size_t>(kRowMaxStages, (200 * 1024 - 256 - w_round) / stage_bytes);
-  const size_t smem = w_round + (size_t)p.stages * stage_bytes + 256;
+  p.stages = (int)std::min<size_t>(kRowMaxStages, (200 * 1024 - 512 - w_round) / stage_bytes);
+  const size_t smem = w_round + (size_t)p.stages * stage_bytes + 512;  // barriers (256 B) + bias (256 B)
   const int grid = p.n_mtiles < n_sms ? p.n_mtiles : n_sms;
   if (cout == 64) {
     FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    conv_rows_tc_kernel<64><<<grid, kConvThreads, smem, s>>>(m0, m1, p);
+    conv_rows_tc_kernel<64><<<grid, kRowsThreads, smem, s>>>(m0, m1, p);
   } else {
     FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    conv_rows_tc_kernel<32><<<grid, kConvThreads, smem, s>>>(m0, m1, p);
+    conv_rows_tc_kernel<32><<<grid, kRowsThreads, smem, s>>>(m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
+  if (d_stats) {
+    std::vector<unsigned long long> h(148 * 16);
+    FSR_CUDA(cudaStreamSynchronize(s));
+    FSR_CUDA(cudaMemcpy(h.data(), d_stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const unsigned long long* c = h.data() + 16 * (grid / 2);
+    fprintf(stderr, "[rows W=%d cin=%d cout=%d tiles=%d] producer total %llu wait-empty %llu | issuer0 total %llu wait-acc %llu wait-full %llu tiles %llu | issuer1 total %llu wait-acc %llu wait-full %llu | epi total %llu wait-acc-full %llu wait+ld %llu\n",
+            W, C0 + C1, cout, p.n_mtiles, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[10], c[11], c[12]);
+  }
 }
 
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
