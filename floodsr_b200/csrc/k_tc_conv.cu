@@ -21,7 +21,9 @@ using namespace tc;
 namespace {
 
 constexpr int kMaxStages = 8;
-constexpr int kConvThreads = 192;
+constexpr int kConvPairs = 2;                           // M tiles one CTA of conv_tc_kernel may compute (sharing the weight slices)
+template <int PAIR>
+constexpr int kConvThreads = 32 + 32 * PAIR + 128;  // producer warp, one MMA warp per M tile, 4 epilogue warps
 
 // MMA with the 64-bit shared-memory descriptors given as 32-bit halves: the issuing lane then only does 32-bit adds per
 // instruction (rebuilding 64-bit descriptors per MMA costs more issue time than a narrow MMA takes to execute)
@@ -52,6 +54,7 @@ struct ConvTcParams {
   float alpha;
   int half;                // 16-bit format: 0 bf16, 1 fp16
   int stages;              // TMA ring depth (as many as fit: deep layers are L2-latency bound per K step)
+  int pair;                // M tiles per CTA (1 or 2)
   int im;                  // 1: image-major tensors ("IM8" [C/8][H*W][N][8], maps of <= 64 pixels): an M tile is 128 images at
                            // one output pixel, each tap is ONE contiguous 2 KB run per channel chunk, out-of-range taps are skipped
   int ncap;                // images per pixel plane of IM8 tensors (allocation capacity)
@@ -62,16 +65,19 @@ struct ConvTcParams {
   __nv_bfloat16* out;          // CP8 output
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN, int PAIR>
+__global__ void __launch_bounds__(kConvThreads<PAIR>, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stages are sized for this layer's K slice (kc 8-channel planes), so narrow layers fit several CTAs per SM and
-  // their TMA latencies overlap
+  // their TMA latencies overlap.  With PAIR == 2 a CTA computes TWO M tiles (adjacent image blocks at the same
+  // output position, so the same taps and weights): every weight slice fetched from L2 feeds two MMAs, one per
+  // accumulator, each issued by its own warp.
   const int kABytesMax = p.kc * 128 * 16;
   const int kBBytesMax = p.kc * BN * 16;
-  uint8_t* smem_a = smem_raw;                                   // p.stages x a_bytes
-  uint8_t* smem_b = smem_raw + p.stages * kABytesMax;            // p.stages x b_bytes
+  const int a_stage = PAIR * kABytesMax;
+  uint8_t* smem_a = smem_raw;                                   // p.stages x pair x a_bytes
+  uint8_t* smem_b = smem_raw + p.stages * a_stage;                // p.stages x b_bytes
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * kBBytesMax);
   uint64_t* full = bars;                // [p.stages]
   uint64_t* empty = bars + p.stages;     // [p.stages]
@@ -81,7 +87,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.ksz * p.ksz;
   const int stages_per_tap = p.s0 + p.s1;
-  const int n_iters = taps * stages_per_tap;
   const uint32_t a_bytes = (uint32_t)p.kc * 128u * 16u;
   const uint32_t b_bytes = (uint32_t)p.kc * BN * 16u;
 
@@ -90,7 +95,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int tx = t % p.tiles_x;
   t /= p.tiles_x;
   const int ty = t % p.tiles_y;
-  const int tn = t / p.tiles_y;
+  const int tn0 = (t / p.tiles_y) * PAIR;
   const int n_tile = blockIdx.y;
   auto tap_ok = [&](int tap) {
     if (!p.im) return true;
@@ -110,13 +115,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       for (int i = 0; i < p.stages; ++i) {
         mbar_init(&full[i], 1);
-        mbar_init(&empty[i], 1);
+        mbar_init(&empty[i], PAIR);
       }
-      mbar_init(accum_full, 1);
+      mbar_init(accum_full, PAIR);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, (uint32_t)(PAIR * BN));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -136,88 +141,105 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], a_bytes + b_bytes);
+          mbar_expect_tx(&full[s], PAIR * a_bytes + b_bytes);
           const bool second = st >= p.s0;
           const CUtensorMap* tm = second ? &tmA1 : &tmA0;
           const int chunk0 = (second ? st - p.s0 : st) * p.kc;
-          if (p.im) tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], tn * 256, (ty + dy) * p.W + tx + dx, chunk0, 0, 0);
-          else tma_load_5d(smem_a + s * kABytesMax, tm, &full[s], 2 * (tx * p.bw + dx), ty * p.bh + dy, tn * p.bn, chunk0, 0);
+          for (int h = 0; h < PAIR; ++h) {  // a block past the last image reads as zeros (TMA bounds fill)
+            uint8_t* dst = smem_a + s * a_stage + h * kABytesMax;
+            if (p.im) tma_load_5d(dst, tm, &full[s], (tn0 + h) * 256, (ty + dy) * p.W + tx + dx, chunk0, 0, 0);
+            else tma_load_5d(dst, tm, &full[s], 2 * (tx * p.bw + dx), ty * p.bh + dy, (tn0 + h) * p.bn, chunk0, 0);
+          }
           const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)p.kc * BN * 8);
           bulk_load_1d(smem_b + s * kBBytesMax, wsrc, b_bytes, &full[s]);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t idesc = idesc_16(128, BN, p.half);
-    const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a), 128 * 16);
-    const uint32_t b_lo0 = desc_lo32(smem_u32(smem_b), BN * 16);
-    const uint32_t a_step = (uint32_t)kABytesMax >> 4, b_step = (uint32_t)kBBytesMax >> 4;
-    const int kpairs = p.kc / 2;
-    const bool leader = elect_one();
-    int s = 0;
-    uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0;
-    for (int it = 0; it < n_iters_cta; ++it) {
-      mbar_wait(&full[s], ph);
-      tc_fence_after();
-      if (leader) {
-        // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
-        for (int j = 0; j < kpairs; ++j)
-          umma_lo(tmem_base, a_lo + j * ((2 * 128 * 16) >> 4), b_lo + j * ((2 * BN * 16) >> 4), kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
-        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
-        if (it == n_iters_cta - 1) umma_commit(accum_full);
+  } else if (warp <= PAIR) {
+    // ===================== MMA issuers: warp 1 + h feeds accumulator h (warp-uniform loop, one elected lane issues) =====================
+    const int h = warp - 1;
+    {
+      const uint32_t idesc = idesc_16(128, BN, p.half);
+      const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a + h * kABytesMax), 128 * 16);
+      const uint32_t b_lo0 = desc_lo32(smem_u32(smem_b), BN * 16);
+      const uint32_t a_step = (uint32_t)a_stage >> 4, b_step = (uint32_t)kBBytesMax >> 4;
+      const uint32_t d = tmem_base + h * BN;
+      const int kpairs = p.kc / 2;
+      const bool leader = elect_one();
+      int s = 0;
+      uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0;
+      for (int it = 0; it < n_iters_cta; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (leader) {
+          // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
+          for (int j = 0; j < kpairs; ++j)
+            umma_lo(d, a_lo + j * ((2 * 128 * 16) >> 4), b_lo + j * ((2 * BN * 16) >> 4), kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+          if (it == n_iters_cta - 1) umma_commit(accum_full);
+        }
+        __syncwarp();
+        a_lo += a_step;
+        b_lo += b_step;
+        if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
       }
-      __syncwarp();
-      a_lo += a_step;
-      b_lo += b_step;
-      if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (4 warps, one per TMEM lane quarter) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int lx = m % p.bw;
     const int ly = (m / p.bw) % p.bh;
     const int ln = m / (p.bw * p.bh);
-    const int n_img = p.im ? tn * 128 + m : tn * p.bn + ln;
-    const bool valid = n_img < p.N;
-    const long long pix = p.im ? ((long long)(ty * p.W + tx) * p.ncap + n_img)
-                               : ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
-    // the residual is fetched while the MMAs still run
-    uint4 resv[BN / 8];
-    if (p.res && valid) {
+    for (int h = 0; h < PAIR; ++h) {
+      const int tn = tn0 + h;
+      const int n_img = p.im ? tn * 128 + m : tn * p.bn + ln;
+      const bool valid = n_img < p.N;
+      const long long pix = p.im ? ((long long)(ty * p.W + tx) * p.ncap + n_img)
+                                 : ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
+      // the first tile's residual is fetched while the MMAs still run
+      uint4 resv[BN / 8];
+      if (p.res && valid) {
+#pragma unroll
+        for (int c = 0; c < BN / 8; ++c) {
+          const int co = n_tile * BN + c * 8;
+          if (co < p.cout) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)(co >> 3) * p.plane + pix) * 8));
+        }
+      }
+      if (h == 0) {
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN;
 #pragma unroll
       for (int c = 0; c < BN / 8; ++c) {
+        float v[8];
+        tmem_ld8(taddr + c * 8, v);
+        tmem_ld_wait();
         const int co = n_tile * BN + c * 8;
-        if (co < p.cout) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)(co >> 3) * p.plane + pix) * 8));
-      }
-    }
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (valid && co < p.cout) {
+          const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.res) {
+            float r[8];
+            unpack_x8(resv[c], r, p.half);
 #pragma unroll
-    for (int c = 0; c < BN / 8; ++c) {
-      float v[8];
-      tmem_ld8(taddr + c * 8, v);
-      tmem_ld_wait();
-      const int co = n_tile * BN + c * 8;
-      if (valid && co < p.cout) {
-        const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            for (int i = 0; i < 8; ++i) v[i] += r[i];
+          }
+          if (p.act == FSR_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+          } else if (p.act == FSR_ACT_LEAKY) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * p.alpha;
+          }
+          *reinterpret_cast<uint4*>(p.out + off) = pack_x8(v, p.half);
         }
-        if (p.res) {
-          float r[8];
-          unpack_x8(resv[c], r, p.half);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += r[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act, p.alpha);
-        *reinterpret_cast<uint4*>(p.out + off) = pack_x8(v, p.half);
       }
     }
     tc_fence_before();
@@ -225,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, (uint32_t)(PAIR * BN));
   }
 }
 
@@ -659,15 +681,15 @@ inline int grid_for(long long total, int threads = 256) {
 }
 
 template <int BN>
-size_t conv_smem_bytes(int kc, int stages) {
-  return (size_t)stages * (kc * 128 * 16) + (size_t)stages * (kc * BN * 16) + (2 * stages + 1) * sizeof(uint64_t) + 16;
+size_t conv_smem_bytes(int kc, int stages, int pair) {
+  return (size_t)stages * pair * (kc * 128 * 16) + (size_t)stages * (kc * BN * 16) + (2 * stages + 1) * sizeof(uint64_t) + 16;
 }
 template <int BN>
-int conv_stages(int kc, int n_iters, long long n_ctas) {
+int conv_stages(int kc, int n_iters, long long n_ctas, int pair) {
   // few CTAs (deep, narrow levels): one CTA per SM with a deep ring, each K step is L2-latency bound;
   // many CTAs: keep two or more CTAs per SM so that their prologues and epilogues overlap
-  const size_t budget = n_ctas <= 2 * 148 ? 200 * 1024 : 100 * 1024;
-  int st = (int)(budget / ((size_t)kc * 128 * 16 + (size_t)kc * BN * 16));
+  const size_t budget = n_ctas <= (pair > 1 ? 148 : 2 * 148) ? 200 * 1024 : 100 * 1024;
+  int st = (int)(budget / ((size_t)pair * kc * 128 * 16 + (size_t)kc * BN * 16));
   st = st > kMaxStages ? kMaxStages : st;
   st = st > n_iters ? n_iters : st;
   return st < 2 ? 2 : st;
@@ -802,22 +824,42 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
                          : make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc);
   const int BN = conv_tc_bn(cout);
   const int n_iters = ksz * ksz * (p.s0 + p.s1);
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)ceil_div(cout, BN));
+  // Two image blocks per CTA (every weight slice fetched from L2 feeds two MMAs) where it measured faster on B200: maps of
+  // <= 16 pixels with enough CTAs left to fill the SMs.  Larger maps have short K loops and many CTAs; there two
+  // co-resident single-tile CTAs (8 epilogue warps per SM instead of 4) win.  env FSR_NO_CONV_PAIR disables it.
+  const long long n_single = (long long)p.tiles_x * p.tiles_y * tiles_n * ceil_div(cout, conv_tc_bn(cout));
+  p.pair = (tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR")) ? kConvPairs : 1;
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * ceil_div(tiles_n, p.pair)), (unsigned)ceil_div(cout, BN));
   if (BN == 128) {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
-    p.stages = conv_stages<128>(kc, n_iters, (long long)grid.x * grid.y);
-    conv_tc_kernel<128><<<grid, kConvThreads, conv_smem_bytes<128>(kc, p.stages), s>>>(m0, m1, p);
+    if (!attr) {
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      attr = true;
+    }
+    p.stages = conv_stages<128>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
+    if (p.pair == 2) conv_tc_kernel<128, 2><<<grid, kConvThreads<2>, conv_smem_bytes<128>(kc, p.stages, 2), s>>>(m0, m1, p);
+    else conv_tc_kernel<128, 1><<<grid, kConvThreads<1>, conv_smem_bytes<128>(kc, p.stages, 1), s>>>(m0, m1, p);
   } else if (BN == 64) {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
-    p.stages = conv_stages<64>(kc, n_iters, (long long)grid.x * grid.y);
-    conv_tc_kernel<64><<<grid, kConvThreads, conv_smem_bytes<64>(kc, p.stages), s>>>(m0, m1, p);
+    if (!attr) {
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      attr = true;
+    }
+    p.stages = conv_stages<64>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
+    if (p.pair == 2) conv_tc_kernel<64, 2><<<grid, kConvThreads<2>, conv_smem_bytes<64>(kc, p.stages, 2), s>>>(m0, m1, p);
+    else conv_tc_kernel<64, 1><<<grid, kConvThreads<1>, conv_smem_bytes<64>(kc, p.stages, 1), s>>>(m0, m1, p);
   } else {
     static bool attr = false;
-    if (!attr) { FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
-    p.stages = conv_stages<32>(kc, n_iters, (long long)grid.x * grid.y);
-    conv_tc_kernel<32><<<grid, kConvThreads, conv_smem_bytes<32>(kc, p.stages), s>>>(m0, m1, p);
+    if (!attr) {
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      attr = true;
+    }
+    p.stages = conv_stages<32>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
+    if (p.pair == 2) conv_tc_kernel<32, 2><<<grid, kConvThreads<2>, conv_smem_bytes<32>(kc, p.stages, 2), s>>>(m0, m1, p);
+    else conv_tc_kernel<32, 1><<<grid, kConvThreads<1>, conv_smem_bytes<32>(kc, p.stages, 1), s>>>(m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
 }
