@@ -2,6 +2,7 @@
 
     python scripts/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/launches_r1.md
     python scripts/ncu_summary.py kernel gpurun_out/prof_head_r1.ncu-rep profiles/head_kernel_ncu.json --tiles 32 --flops-per-tile 4.998e9
+    (--index k picks the k-th captured launch of a multi-kernel report)
 """
 import csv
 import json
@@ -40,10 +41,10 @@ def launches(src, dst):
     print("wrote", dst)
 
 
-def kernel(src, dst, tiles, flops_per_tile):
+def kernel(src, dst, tiles, flops_per_tile, index=0):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + index]  # one row per captured launch
     want = [
         "Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "launch__registers_per_thread",
@@ -84,4 +85,5 @@ if __name__ == "__main__":
     else:
         tiles = int(sys.argv[sys.argv.index("--tiles") + 1])
         fpt = float(sys.argv[sys.argv.index("--flops-per-tile") + 1])
-        kernel(sys.argv[2], sys.argv[3], tiles, fpt)
+        idx = int(sys.argv[sys.argv.index("--index") + 1]) if "--index" in sys.argv else 0
+        kernel(sys.argv[2], sys.argv[3], tiles, fpt, idx)
