@@ -72,6 +72,7 @@ SIGNATURES = {
         [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "fsr_band_finalize_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "fsr_band_finalize_rows_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "fsr_band_host_begin": (C.c_int, [_H, _F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _F, C.c_void_p]),
     "fsr_band_host_end": (C.c_int, [_H, C.c_void_p, C.c_int32, _U]),
     "fsr_fetch_flags": (C.c_int, [_H, C.c_void_p, _U]),

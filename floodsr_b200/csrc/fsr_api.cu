@@ -434,12 +434,16 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
 }
 
 static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s,
-                          const DeviceBuf* tiles_buf = nullptr, const BandState* st = nullptr) {
+                          const DeviceBuf* tiles_buf = nullptr, const BandState* st = nullptr, int row_begin = 0, int row_end = -1) {
   BlendGeom g = e.blend_geom();
   const BandState& b = st ? *st : e.band;
   const DeviceBuf& tiles = tiles_buf ? *tiles_buf : e.d_tiles;
+  if (row_end < 0) row_end = b.n_rows;
+  if (row_end <= row_begin) return;
+  const bool first = row_begin == 0;  // only the band's first rows start from the previous band's partial sums
   ProfScope scope(e.prof, PROF_BLEND, s);
-  launch_blend(tiles.as<float>(), b.ty0, b.ty1, g, b.row0, b.n_rows, d_halo_in, halo_rows_in, true, b.max_depth, d_out_rows, s);
+  launch_blend(tiles.as<float>(), b.ty0, b.ty1, g, b.row0 + row_begin, row_end - row_begin, first ? d_halo_in : nullptr,
+               first ? halo_rows_in : 0, true, b.max_depth, d_out_rows + (size_t)row_begin * g.W, s);
 }
 
 }  // namespace fsr
@@ -720,6 +724,19 @@ int fsr_band_run_dev(fsr_engine* eng, const float* d_depth_lr, const float* d_de
   FSR_REQUIRE(!e.win.ys.empty(), "fsr_set_windows has not been called");
   FSR_REQUIRE(d_depth_lr && d_dem_hr, "NULL device buffer");
   band_run(e, d_depth_lr, d_dem_hr, band_row0, band_rows_hr, ty0, ty1, *params, d_halo_out, d_stats, (cudaStream_t)stream);
+  FSR_API_END()
+}
+
+int fsr_band_finalize_rows_dev(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows_in, float* d_out_rows,
+                               int32_t row_begin, int32_t row_end, void* stream) {
+  FSR_API_BEGIN(eng)
+  FSR_REQUIRE(d_out_rows != nullptr, "NULL device buffer");
+  Engine& e = eng->impl;
+  FSR_REQUIRE(e.band.ty1 > e.band.ty0, "fsr_band_run_dev has not been called");
+  FSR_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= e.band.n_rows, "row range outside the band");
+  FSR_REQUIRE(row_begin == 0 ? halo_rows_in <= row_end : halo_rows_in <= row_begin,
+              "the rows that start from the previous band's sums must lie in one call");
+  band_finalize(e, d_halo_in, halo_rows_in, d_out_rows, (cudaStream_t)stream, nullptr, nullptr, row_begin, row_end);
   FSR_API_END()
 }
 

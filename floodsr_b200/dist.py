@@ -79,6 +79,19 @@ def exchange_halo(plan: BandPlan, plans: list[BandPlan], halo_out, make_recv, di
     return recv
 
 
+def start_halo_exchange(plan: BandPlan, plans: list[BandPlan], halo_out, make_recv, dist_mod, group=None):
+    """`exchange_halo` without the wait: returns (receive tensor or None, outstanding requests)."""
+    ops = []
+    recv = None
+    nxt = plan.rank + 1
+    if not plan.empty and plan.halo_out_rows > 0 and nxt < len(plans) and not plans[nxt].empty:
+        ops.append(dist_mod.P2POp(dist_mod.isend, halo_out, nxt, group=group))
+    if not plan.empty and plan.halo_in_rows > 0 and plan.rank > 0:
+        recv = make_recv(plan.halo_in_rows)
+        ops.append(dist_mod.P2POp(dist_mod.irecv, recv, plan.rank - 1, group=group))
+    return recv, (dist_mod.batch_isend_irecv(ops) if ops else [])
+
+
 class CudaBandExecutor:
     """Band arithmetic on the CUDA engine: inputs/outputs are torch CUDA tensors owned by the caller."""
 
@@ -150,6 +163,22 @@ class CudaBandExecutor:
         )
         return out_rows
 
+    def band_finalize_rows(self, plan: BandPlan, halo_in, out_rows, row_begin: int, row_end: int):
+        """`band_finalize` for the band-relative rows [row_begin, row_end) only (out_rows always spans the whole band)."""
+        torch = self.torch
+        if out_rows is None:
+            out_rows = torch.empty((plan.n_rows, self.w), dtype=torch.float32, device=self.device)
+        assert out_rows.shape == (plan.n_rows, self.w) and out_rows.is_contiguous()
+        if row_end > row_begin:
+            self._lib_mod.check(
+                self.lib.fsr_band_finalize_rows_dev(
+                    self.engine._handle, C.c_void_p(halo_in.data_ptr()) if halo_in is not None else None,
+                    int(halo_in.shape[0]) if halo_in is not None else 0, C.c_void_p(out_rows.data_ptr()), int(row_begin),
+                    int(row_end), self._stream(),
+                )
+            )
+        return out_rows
+
     def make_recv(self, rows: int):
         return self.torch.empty((rows, self.w), dtype=self.torch.float32, device=self.device)
 
@@ -211,5 +240,15 @@ def run_band_step(executor, plan: BandPlan, plans: list[BandPlan], depth_band, d
     halo_out = executor.band_run(plan, depth_band, dem_band, band_row0)
     halo_in = None
     if dist_mod is not None and len(plans) > 1:
+        if hasattr(executor, "band_finalize_rows"):
+            # the rows below the shared ones do not depend on the previous rank: blend them while the halo is in flight
+            halo_in, reqs = start_halo_exchange(plan, plans, halo_out, executor.make_recv, dist_mod, group)
+            split = plan.halo_in_rows if halo_in is not None else 0
+            out_rows = executor.band_finalize_rows(plan, None, out_rows, split, plan.n_rows)
+            for req in reqs:
+                req.wait()
+            if split > 0:
+                executor.band_finalize_rows(plan, halo_in, out_rows, 0, split)
+            return out_rows
         halo_in = exchange_halo(plan, plans, halo_out, executor.make_recv, dist_mod, group)
     return executor.band_finalize(plan, halo_in, out_rows)

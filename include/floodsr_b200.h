@@ -133,6 +133,9 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
  *                          the previous band's partial sums d_halo_in [halo_rows_in, W] (NULL for the first
  *                          band) and continue in the reference's window order, so the sharded result is
  *                          bit-identical to the single-GPU one; weights are analytic and never exchanged.
+ *   fsr_band_finalize_rows_dev  the same for the band-relative rows [row_begin, row_end) only (d_out_rows still points
+ *                          at the band's first row): rows >= halo_rows_in do not depend on the previous band, so a rank
+ *                          can blend them while the halo exchange is in flight and the first halo_rows_in rows after it.
  * With ty0 = 0, ty1 = ny the sequence equals fsr_run_raster without the host copies. */
 int fsr_set_windows(fsr_engine* eng, int32_t H, int32_t W, int32_t window_method, int32_t overlap_hr,
                     const int32_t* y_starts, int32_t ny, const int32_t* x_starts, int32_t nx, const float* ramp,
@@ -144,6 +147,8 @@ int fsr_band_run_dev(fsr_engine* eng, const float* d_depth_lr, const float* d_de
                      float* d_halo_out, float* d_stats, void* stream);
 int fsr_band_finalize_dev(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows_in, float* d_out_rows,
                           void* stream);
+int fsr_band_finalize_rows_dev(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows_in, float* d_out_rows,
+                               int32_t row_begin, int32_t row_end, void* stream);
 /* Host-buffer, pipelined variant for one rank's band (new; used by bench.py's multi-GPU end-to-end leg and by
  * floodsr_b200/dist.py): depth_lr / dem_hr / out_rows are (page-locked) host buffers holding the raster rows from HR row
  * band_row0 on and the rows the band owns; sub-bands overlap H2D, kernels and D2H like fsr_run_raster.

@@ -303,8 +303,9 @@ def test_run_raster_input_assertions(engine):
 # ---------------------------------------------------------------------------------------------------------
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("h,w,world", [(2048, 1024, 2), (1552, 1040, 3), (4096, 1024, 4)])
-def test_band_sharding_is_bit_identical_to_single_pass(engine, h, w, world):
+def test_band_sharding_is_bit_identical_to_single_pass(engine, h, w, world, split):
     import torch
 
     from floodsr_b200.dist import CudaBandExecutor, plan_bands
@@ -324,7 +325,14 @@ def test_band_sharding_is_bit_identical_to_single_pass(engine, h, w, world):
         depth_band = torch.from_numpy(depth[r0 // 16 : (r0 + plan.in_rows + 15) // 16]).to(dev).contiguous()
         halo_out = ex.band_run(plan, depth_band, dem_band, r0)
         assert (halo is None) == (plan.halo_in_rows == 0)
-        rows = ex.band_finalize(plan, halo)
+        if split:
+            # what run_band_step does under a process group: the rows below the shared ones first, the shared ones last
+            k = plan.halo_in_rows
+            rows = ex.band_finalize_rows(plan, None, None, k, plan.n_rows)
+            if k > 0:
+                ex.band_finalize_rows(plan, halo, rows, 0, k)
+        else:
+            rows = ex.band_finalize(plan, halo)
         ex.check_flags()
         got[plan.row0 : plan.row0 + plan.n_rows] = rows.cpu().numpy()
         halo = halo_out
