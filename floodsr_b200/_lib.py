@@ -76,6 +76,11 @@ SIGNATURES = {
     "fsr_band_host_begin": (C.c_int, [_H, _F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _F, C.c_void_p]),
     "fsr_band_host_end": (C.c_int, [_H, C.c_void_p, C.c_int32, _U]),
     "fsr_fetch_flags": (C.c_int, [_H, C.c_void_p, _U]),
+    "fsr_resample_bilinear": (C.c_int, [_H, _F, C.c_int32, C.c_int32, _F, C.c_int32, C.c_int32, C.c_void_p]),
+    "fsr_resample_bilinear_dev": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
     "fsr_stage_normalize": (C.c_int, [_H, _F, _F, C.c_int32, _P, _F, _F, _F, _U]),
     "fsr_stage_forward": (C.c_int, [_H, _F, _F, C.c_int32, _F]),
     "fsr_stage_invert": (C.c_int, [_H, _F, C.c_size_t, C.c_float, C.c_float, _F]),
@@ -90,6 +95,16 @@ SIGNATURES = {
     "fsr_host_alloc": (C.c_void_p, [C.c_size_t]),
     "fsr_host_free": (None, [C.c_void_p]),
 }
+
+class ResampleParams(C.Structure):
+    """fsr_resample_params of include/floodsr_b200.h."""
+
+    _fields_ = [
+        ("x_a_dst", C.c_double), ("x_c_dst", C.c_double), ("x_a_src", C.c_double), ("x_c_src", C.c_double),
+        ("y_a_dst", C.c_double), ("y_c_dst", C.c_double), ("y_a_src", C.c_double), ("y_c_src", C.c_double),
+        ("has_src_nodata", C.c_int32), ("src_nodata", C.c_float), ("dst_fill", C.c_float),
+    ]
+
 
 _lib = None
 

@@ -872,6 +872,39 @@ int fsr_band_host_end(fsr_engine* eng, const float* d_halo_in, int32_t halo_rows
   FSR_API_END()
 }
 
+static void check_resample(const fsr_resample_params* p, int sh, int sw, int dh, int dw) {
+  FSR_REQUIRE(p != nullptr, "params is NULL");
+  FSR_REQUIRE(sh > 0 && sw > 0 && dh > 0 && dw > 0, "empty raster");
+  FSR_REQUIRE(p->x_a_src != 0.0 && p->y_a_src != 0.0 && p->x_a_dst != 0.0 && p->y_a_dst != 0.0, "degenerate transform");
+  const double xs = fabs(p->x_a_src / p->x_a_dst), ys = fabs(p->y_a_src / p->y_a_dst);
+  FSR_REQUIRE(xs >= 1.0 / 64 && ys >= 1.0 / 64, "down-sampling by more than 64x is not supported");
+}
+
+int fsr_resample_bilinear_dev(fsr_engine* eng, const float* d_src, int32_t sh, int32_t sw, float* d_dst, int32_t dh, int32_t dw,
+                              const fsr_resample_params* params, void* stream) {
+  FSR_API_BEGIN(eng)
+  FSR_REQUIRE(d_src && d_dst, "NULL device buffer");
+  check_resample(params, sh, sw, dh, dw);
+  launch_resample_bilinear(d_src, sh, sw, d_dst, dh, dw, *params, (cudaStream_t)stream);
+  FSR_API_END()
+}
+
+int fsr_resample_bilinear(fsr_engine* eng, const float* src, int32_t sh, int32_t sw, float* dst, int32_t dh, int32_t dw,
+                          const fsr_resample_params* params) {
+  FSR_API_BEGIN(eng)
+  Engine& e = eng->impl;
+  FSR_REQUIRE(src && dst, "NULL host buffer");
+  check_resample(params, sh, sw, dh, dw);
+  cudaStream_t s = 0;
+  e.d_in_dem.ensure((size_t)sh * sw * sizeof(float));
+  e.d_out.ensure((size_t)dh * dw * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(e.d_in_dem.p, src, (size_t)sh * sw * sizeof(float), cudaMemcpyHostToDevice, s));
+  launch_resample_bilinear(e.d_in_dem.as<float>(), sh, sw, e.d_out.as<float>(), dh, dw, *params, s);
+  FSR_CUDA(cudaMemcpyAsync(dst, e.d_out.p, (size_t)dh * dw * sizeof(float), cudaMemcpyDeviceToHost, s));
+  FSR_CUDA(cudaStreamSynchronize(s));
+  FSR_API_END()
+}
+
 int fsr_fetch_flags(fsr_engine* eng, void* stream, uint32_t* out_flags) {
   FSR_API_BEGIN(eng)
   unsigned f = eng->impl.fetch_flags((cudaStream_t)stream);

@@ -63,6 +63,9 @@ void launch_invert_depth(const float* pred_norm, float* pred_m, size_t n, float 
 void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, int row0, int n_rows, const float* d_init,
                   int init_rows, bool finalize, float max_depth, float* d_out, cudaStream_t s);
 
+void launch_resample_bilinear(const float* d_src, int sh, int sw, float* d_dst, int dh, int dw, const fsr_resample_params& p,
+                              cudaStream_t s);
+
 // Window grid of one raster pass, resident on the device.
 struct WindowGrid {
   int H = 0, W = 0, T = 0, overlap = 0, method = 0;

@@ -144,9 +144,49 @@ class ModelWorkerB200:
                                      model_scale=model_scale, contract_hr_tile=contract_hr_tile, window_method=window_method,
                                      overlap_lr=overlap_lr)
 
+    def run_raw_grids(self, depth_lr: np.ndarray, depth_bounds, dem_crop: np.ndarray, dem_crop_transform, *, dem_nodata=None,
+                      max_depth: float | None = None, dem_pct_clip: float | None = None, window_method: str = "feather",
+                      tile_overlap: int | None = None, tile_size: int | None = None) -> dict[str, Any]:
+        """`ModelWorker.run` between the raster reads and the raster write, with both grid changes on the GPU (section 8f#2).
+
+        `depth_lr`: low-resolution depth on its native grid (nodata already replaced, `preprocessing.py:343-347`);
+        `depth_bounds` = (west, south, east, north) of that raster; `dem_crop` / `dem_crop_transform`: the DEM clipped to
+        those bounds on its own grid (`:352-360`).  Steps: DEM -> model grid (`:367-398`), tile loop + mosaic, prediction
+        -> raw DEM grid (`ResUNet_16x_DEM.py:552-573`), clip and low-depth mask (`:575-583`).
+        """
+        from floodsr_b200.resample import align_dem_to_model_grid, prediction_to_raw_grid  # noqa: PLC0415
+
+        start = time.perf_counter()
+        assert self.engine is not None, "worker must be used under context management"
+        depth_lr = np.asarray(depth_lr, dtype=np.float32)
+        dem_crop = np.asarray(dem_crop, dtype=np.float32)
+        assert dem_crop.size > 0, "clipped DEM is empty"
+        if not np.isfinite(depth_lr).all():
+            raise AssertionError("low-res depth contains non-finite values")
+        if depth_lr.min() < 0.0:
+            raise AssertionError(f"low-res depth has negative values: min={float(depth_lr.min())}")
+        if self.engine.contract is None:
+            self.engine.load()
+        scale = int(self.engine.contract.scale)
+        aligned = align_dem_to_model_grid(self.engine, dem_crop, dem_crop_transform, depth_bounds, depth_lr.shape, scale, dem_nodata)
+        res = self.run_prepared(depth_lr, aligned["dem_hr"], max_depth=max_depth, dem_pct_clip=dem_pct_clip, window_method=window_method,
+                                tile_overlap=tile_overlap, tile_size=tile_size, _postprocess=False)
+        prediction_model_m = res["prediction_m"]
+        post_resampled = tuple(dem_crop.shape) != tuple(prediction_model_m.shape)
+        prediction_out_m = prediction_to_raw_grid(self.engine, prediction_model_m, aligned["dem_hr_transform"], dem_crop.shape, dem_crop_transform)
+        res["prediction_m"] = postprocess_depth(prediction_out_m, float(res["preprocess"]["max_depth"]), self.low_depth_mask_m)
+        res["runtime_s"] = float(time.perf_counter() - start)
+        res["preprocess"]["resampled"] = bool(aligned["resampled"])
+        res["preprocess"]["post_resampled"] = bool(post_resampled)
+        res["preprocess"]["input_shape"].update(
+            crop_height=int(res["prediction_m"].shape[0]), crop_width=int(res["prediction_m"].shape[1]),
+            output_shape=[int(x) for x in res["prediction_m"].shape],
+        )
+        return res
+
     def run_prepared(self, depth_lr_prepared: np.ndarray, dem_hr_prepared: np.ndarray, *, max_depth: float | None = None,
                      dem_pct_clip: float | None = None, window_method: str = "feather", tile_overlap: int | None = None,
-                     tile_size: int | None = None) -> dict[str, Any]:
+                     tile_size: int | None = None, _postprocess: bool = True) -> dict[str, Any]:
         """The array part of `ModelWorker.run` for prepared (aligned, model-space) rasters."""
         start = time.perf_counter()
         assert self.engine is not None, "worker must be used under context management"
@@ -161,7 +201,7 @@ class ModelWorkerB200:
         )
         dem_shape = tuple(np.asarray(dem_hr_prepared).shape)
         assert prediction_model_m.shape == dem_shape, f"prediction shape {prediction_model_m.shape} must match preprocessed DEM shape {dem_shape}"
-        prediction_out_m = postprocess_depth(prediction_model_m, float(cfg["max_depth"]), self.low_depth_mask_m)
+        prediction_out_m = postprocess_depth(prediction_model_m, float(cfg["max_depth"]), self.low_depth_mask_m) if _postprocess else prediction_model_m
         return {
             "prediction_m": prediction_out_m,
             "runtime_s": float(time.perf_counter() - start),

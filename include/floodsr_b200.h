@@ -80,6 +80,19 @@ typedef struct fsr_tile_params {
   float ref_dem_max;
 } fsr_tile_params;
 
+/* Bilinear change of grid (SURVEY.md section 8 f#2): the two rasterio.warp.reproject(..., Resampling.bilinear) calls of the
+ * reference, floodsr/preprocessing.py:371-387 (raw DEM grid -> model grid) and
+ * floodsr/models/ResUNet_16x_DEM.py:554-573 (prediction -> raw DEM grid), for north-up grids in one CRS.
+ * Source coordinate of destination column i: ((x_a_dst * (i + 0.5) + x_c_dst) - x_c_src) / x_a_src with the
+ * (a, c) / (e, f) terms of the two affine transforms; rows likewise. */
+typedef struct fsr_resample_params {
+  double x_a_dst, x_c_dst, x_a_src, x_c_src;
+  double y_a_dst, y_c_dst, y_a_src, y_c_src;
+  int32_t has_src_nodata;   /* source pixels equal to src_nodata are skipped and the weights renormalised */
+  float src_nodata;
+  float dst_fill;           /* value of destination pixels nothing maps to (dst_nodata, 0 when there is none) */
+} fsr_resample_params;
+
 /* ---- lifecycle -------------------------------------------------------------------------------------
  * Replaces EngineORT.__init__/load (ort.py:31-59): `plan` is the lowered layer list and `weights` the
  * float32 initializer blob produced by floodsr_b200/graph.py from model_infer.onnx. */
@@ -198,6 +211,14 @@ int fsr_debug_read_tensor(fsr_engine* eng, int32_t tensor, int32_t n_tiles, floa
 /* Pinned host memory for callers that want full-speed H2D/D2H through the host entry points. */
 void* fsr_host_alloc(size_t bytes);
 void fsr_host_free(void* p);
+
+/* ---- grid change (section 8 f#2) ---------------------------------------------------------------------
+ * fsr_resample_bilinear      host buffers: src [sh, sw] -> dst [dh, dw] (copies in, kernel, copy out).
+ * fsr_resample_bilinear_dev  device buffers on `stream`, for callers that keep the rasters resident. */
+int fsr_resample_bilinear(fsr_engine* eng, const float* src, int32_t sh, int32_t sw, float* dst, int32_t dh, int32_t dw,
+                          const fsr_resample_params* params);
+int fsr_resample_bilinear_dev(fsr_engine* eng, const float* d_src, int32_t sh, int32_t sw, float* d_dst, int32_t dh,
+                              int32_t dw, const fsr_resample_params* params, void* stream);
 
 #ifdef __cplusplus
 }

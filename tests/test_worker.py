@@ -70,3 +70,35 @@ def test_worker_run_prepared_matches_oracle(h1_model_fp):
     assert got.dtype == np.float32 and got.shape == want.shape
     assert np.abs(got - want).max() <= 1e-3  # 1e-4 m model tolerance; a pixel at the 1 mm mask edge may flip to 0
     assert ((got == 0) != (want == 0)).mean() < 1e-4
+
+
+@pytest.mark.gpu
+def test_worker_run_raw_grids_matches_oracle_composition(h1_model_fp):
+    """Section 8f#2: DEM on a 15x grid -> model grid (16x) -> tile loop -> prediction back on the DEM's own grid."""
+    from floodsr_b200.resample import bounds_to_transform
+    from floodsr_b200.worker import ModelWorkerB200
+    from oracle.engine_ref import OracleEngine
+    from oracle.resample_np import resample_bilinear
+    from oracle.stitch_np import run_tiled
+
+    depth, dem_model_like = synth_raster(1024, 1024, seed=11)     # depth 64 x 64
+    bounds = (500.0, 800.0, 500.0 + 1024.0, 800.0 + 1024.0)
+    t_raw = bounds_to_transform(*bounds, 960, 960)
+    t_model = bounds_to_transform(*bounds, 1024, 1024)
+    dem_raw = resample_bilinear(dem_model_like, t_model, (960, 960), t_raw)   # any terrain on the raw grid will do
+    dem_raw[100:110, 200:230] = -9999.0
+    # oracle composition
+    dem_model = resample_bilinear(dem_raw, t_raw, (1024, 1024), t_model, -9999.0, -9999.0)
+    dem_model = np.where(np.isclose(dem_model, -9999.0), 0.0, dem_model).astype(np.float32)
+    pred_model, n_tiles, _ = run_tiled(OracleEngine(h1_model_fp), depth, dem_model, window_method="feather", overlap_lr=8)
+    want = resample_bilinear(pred_model, t_model, (960, 960), t_raw)
+    want = np.where(np.clip(want, 0.0, 5.0) < 1e-3, 0.0, np.clip(want, 0.0, 5.0)).astype(np.float32)
+    with ModelWorkerB200(h1_model_fp, precision="fp32") as worker:
+        res = worker.run_raw_grids(depth, bounds, dem_raw, t_raw, dem_nodata=-9999.0)
+    pre = res["preprocess"]
+    assert pre["resampled"] and pre["post_resampled"] and pre["tile_cache_size"] == n_tiles
+    assert pre["input_shape"]["output_shape"] == [960, 960] and pre["input_shape"]["model_space_crop_height"] == 1024
+    got = res["prediction_m"]
+    assert got.dtype == np.float32 and got.shape == (960, 960)
+    assert np.abs(got - want).max() <= 1e-3
+    assert ((got == 0) != (want == 0)).mean() < 1e-4
