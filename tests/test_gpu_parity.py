@@ -468,3 +468,52 @@ def test_tc_run_raster_ragged_and_hard(tc_engine, oracle_engine, h, w, method):
     got, got_n, got_summary = tc_engine.run_raster(depth, dem, window_method=method)
     assert got.shape == (h, w) and got_n == n_tiles and got_summary == summary
     _assert_tc_close(tc_engine, got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE sizes in the tensor-core mode the bench runs (fp16 operands): size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.fixture(scope="module")
+def fp16_engine(h1_model_fp):
+    from floodsr_b200.engine import EngineB200
+
+    eng = EngineB200(h1_model_fp, precision="fp16")
+    yield eng
+    eng.close()
+
+
+def test_bench_size_raster_is_periodic_for_periodic_inputs(fp16_engine):
+    """bench.py's workload size (4096 x 32768, 935 feather windows).  The inputs repeat every 384 columns (the window
+    stride), so every interior window column sees the same pixels: its predictions, and therefore the mosaic, must repeat
+    bit for bit with the same period — whatever chunk, image block or CTA a window lands in."""
+    h, w, period = 4096, 32768, 384
+    depth_p, dem_p = synth_raster(h, period, seed=21)
+    reps = -(-w // period)
+    dem = np.ascontiguousarray(np.tile(dem_p, (1, reps))[:, :w])
+    depth = np.ascontiguousarray(np.tile(depth_p, (1, reps))[:, : w // 16])
+    out, n_tiles, _ = fp16_engine.run_raster(depth, dem)
+    assert n_tiles == 935 and out.shape == (h, w) and np.isfinite(out).all() and out.min() >= 0.0 and out.max() <= 5.0
+    ref = out[:, 2 * period: 3 * period]
+    for k in (3, 10, 41, 60, 82):   # windows k-1 and k are interior (not the first / forced last window column)
+        assert np.array_equal(out[:, k * period: (k + 1) * period], ref), k
+    again, _, _ = fp16_engine.run_raster(depth, dem)
+    assert np.array_equal(out, again)
+
+
+def test_batch_256_equals_single_tiles_in_tensor_core_mode(fp16_engine):
+    """BASELINE config 3 (256 independent tiles): a tile's result does not depend on the batch it travels in."""
+    from floodsr_b200.synth import synth_tile
+
+    base = [synth_tile(s) for s in range(8)]
+    depth = np.stack([base[i % 8][0] for i in range(256)])
+    dem = np.stack([base[i % 8][1] for i in range(256)])
+    for i in range(8, 256):                      # make the tiles distinct: shift the terrain, scale the depth
+        dem[i] = dem[i] + np.float32(0.37 * i)
+        depth[i] = depth[i] * np.float32(1.0 + 0.001 * i)
+    batch = fp16_engine.run_tiles(depth, dem, want_norm=False)
+    for i in (0, 7, 8, 100, 127, 128, 255):
+        one = fp16_engine.run_tile(depth[i], dem[i])
+        assert np.array_equal(batch["prediction_m"][i], one["prediction_m"]), i
+        assert batch["dem_stats_used"][i] == one["dem_stats_used"]
