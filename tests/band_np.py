@@ -91,5 +91,19 @@ class NumpyBandExecutor:
         out = np.clip(sr[:, : self.w], 0.0, self.max_depth).astype(np.float32)
         return torch.from_numpy(out)
 
+    def band_finalize_rows(self, plan, halo_in, out_rows, row_begin, row_end):
+        """Semantics of fsr_band_finalize_rows_dev: only the band-relative rows [row_begin, row_end) are written; the rows
+        that start from the previous band's sums (the first halo_in rows) must come in the call with row_begin == 0."""
+        if out_rows is None:
+            out_rows = torch.empty((plan.n_rows, self.w), dtype=torch.float32)
+        if row_end <= row_begin:
+            return out_rows
+        assert halo_in is None or (row_begin == 0 and halo_in.shape[0] <= row_end)
+        full = self.band_finalize(plan, halo_in if row_begin == 0 else None)
+        if row_begin > 0 and plan.halo_in_rows > 0:
+            assert row_begin >= plan.halo_in_rows, "rows below the shared ones only"
+        out_rows[row_begin:row_end] = full[row_begin:row_end]
+        return out_rows
+
     def make_recv(self, rows):
         return torch.empty((rows, self.w), dtype=torch.float32)
