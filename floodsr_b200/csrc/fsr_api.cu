@@ -344,6 +344,26 @@ void Engine::setup_windows(int H, int W, int method, int overlap, const int* ys,
     win.d_ramp.ensure((size_t)T * sizeof(float));
     FSR_CUDA(cudaMemcpyAsync(win.d_ramp.p, ramp, (size_t)T * sizeof(float), cudaMemcpyHostToDevice, s));
   }
+  // weight of the first / second covering window at every coordinate: the feather ramp with the scene-edge flattening of
+  // ResUNet_16x_DEM.py:344-352 (the values k_blend.cu's edge_weight() returns), looked up once here instead of per pixel
+  win.Hpad = Hpad; win.Wpad = Wpad;
+  auto weights = [&](const std::vector<int>& st, int pad, const std::vector<int>& first, const std::vector<int>& count) {
+    std::vector<float> tab((size_t)2 * pad, 1.0f);
+    const int n = (int)st.size();
+    for (int c = 0; c < pad; ++c)
+      for (int d = 0; d < 2 && d < count[c]; ++d) {
+        const int idx = first[c] + d, local = c - st[idx];
+        float w = 1.0f;
+        if (win.has_ramp && !(idx == 0 && local < overlap) && !(idx == n - 1 && local >= T - overlap)) w = ramp[local];
+        tab[(size_t)d * pad + c] = w;
+      }
+    return tab;
+  };
+  const std::vector<float> wy_tab = weights(win.ys, Hpad, yf, yc), wx_tab = weights(win.xs, Wpad, xf, xc);
+  win.d_wy_tab.ensure(wy_tab.size() * sizeof(float));
+  win.d_wx_tab.ensure(wx_tab.size() * sizeof(float));
+  FSR_CUDA(cudaMemcpyAsync(win.d_wy_tab.p, wy_tab.data(), wy_tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(win.d_wx_tab.p, wx_tab.data(), wx_tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   // the host vectors above are pageable temporaries: make sure the copies are done before they die
   FSR_CUDA(cudaStreamSynchronize(s));
 }
@@ -365,6 +385,10 @@ BlendGeom Engine::blend_geom() const {
   g.W = win.W;
   g.vec_ok = win.vec_ok ? 1 : 0;
   g.max_cover = win.max_cover;
+  g.wy_tab = win.d_wy_tab.as<float>();
+  g.wx_tab = win.d_wx_tab.as<float>();
+  g.Hpad = win.Hpad;
+  g.Wpad = win.Wpad;
   return g;
 }
 

@@ -20,6 +20,11 @@ struct BlendGeom {
   int H, W;              // cropped output extent
   int vec_ok;            // window x-origins are multiples of 4: float4 path allowed
   int max_cover;         // largest number of window rows / columns covering one coordinate
+  // per-coordinate tables for the fast kernel (max_cover <= 2): weight of the first / second covering window at a
+  // coordinate ([2][pad], same values edge_weight() returns, 1 for the hard method) -- rows and columns
+  const float* wy_tab;
+  const float* wx_tab;
+  int Hpad, Wpad;
 };
 
 
@@ -72,11 +77,12 @@ struct WindowGrid {
   std::vector<int> ys, xs;
   bool vec_ok = true;  // all window x-origins are multiples of 4 pixels
   int max_cover = 1;   // largest number of window rows / columns covering one coordinate
-  DeviceBuf d_ys, d_xs, d_ramp, d_yfirst, d_ycount, d_xfirst, d_xcount, d_origins;
+  DeviceBuf d_ys, d_xs, d_ramp, d_yfirst, d_ycount, d_xfirst, d_xcount, d_origins, d_wy_tab, d_wx_tab;
+  int Hpad = 0, Wpad = 0;
   bool has_ramp = false;
   void release() {
     d_ys.release(); d_xs.release(); d_ramp.release(); d_yfirst.release(); d_ycount.release();
-    d_xfirst.release(); d_xcount.release(); d_origins.release();
+    d_xfirst.release(); d_xcount.release(); d_origins.release(); d_wy_tab.release(); d_wx_tab.release();
   }
 };
 
