@@ -25,7 +25,11 @@ for i, op in enumerate(lm.ops):
         continue
     h, w, c = lm.tensors[t]
     nt = min(n, 4) if h * w * c > 512 * 512 else n
-    a = e32.debug_tensor(t, nt); b = e16.debug_tensor(t, nt)
+    try:
+        a = e32.debug_tensor(t, nt); b = e16.debug_tensor(t, nt)
+    except ValueError as exc:  # tensors the fused high-resolution kernel never materialises
+        print(f"op {i:2d} {_OP_NAMES[op.kind]:8s} t{t:<3d} skipped: {exc}")
+        continue
     err = np.abs(a - b); scale = np.abs(a).max() + 1e-9
     print(f"op {i:2d} {_OP_NAMES[op.kind]:8s} t{t:<3d} {str(lm.tensors[t]):18s} max|a|={scale:9.4f} maxerr={err.max():9.5f} rel={err.max()/scale:8.5f} meanerr={err.mean():9.6f}")
     if err.max() / scale > 0.05:
