@@ -620,16 +620,13 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   e.d_out.ensure((size_t)H * W * sizeof(float));
   e.d_stats.ensure((size_t)ny * nx * 3 * sizeof(float));
   // band plan: enough windows per band to keep the batched layer kernels efficient, small enough to overlap copies;
-  // the first and the last band are a single window row, so the pipeline fills (first H2D) and drains (last D2H) fast
+  // the first band is a single window row, so the pipeline fills fast (first H2D); a single-row LAST band was measured
+  // slower than letting the last band keep its two rows (small batches run the LR layers at a third of their throughput)
   int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
   std::vector<int> band_ty;  // band b covers window rows [band_ty[b], band_ty[b + 1])
   band_ty.push_back(0);
-  if (ny >= 3 && rows_per_band > 1) {
-    band_ty.push_back(1);
-    while (band_ty.back() < ny - 1) band_ty.push_back(std::min(band_ty.back() + rows_per_band, (int)ny - 1));
-  } else {
-    while (band_ty.back() + rows_per_band < ny) band_ty.push_back(band_ty.back() + rows_per_band);
-  }
+  if (ny >= 3 && rows_per_band > 1) band_ty.push_back(1);
+  while (band_ty.back() + rows_per_band < ny) band_ty.push_back(band_ty.back() + rows_per_band);
   band_ty.push_back(ny);
   const int n_bands = (int)band_ty.size() - 1;
   e.d_halo[0].ensure((size_t)T * W * sizeof(float));
@@ -812,16 +809,12 @@ int fsr_band_host_begin(fsr_engine* eng, const float* depth_lr, const float* dem
     FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, sc_));
     FSR_CUDA(cudaStreamSynchronize(sc_));
   }
-  // sub-band plan: single window rows first and last, like fsr_run_raster
+  // sub-band plan: a single window row first, like fsr_run_raster
   const int n_rows_rank = ty1 - ty0;
   int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
   std::vector<int> band_ty{ty0};
-  if (n_rows_rank >= 3 && rows_per_band > 1) {
-    band_ty.push_back(ty0 + 1);
-    while (band_ty.back() < ty1 - 1) band_ty.push_back(std::min(band_ty.back() + rows_per_band, (int)ty1 - 1));
-  } else {
-    while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
-  }
+  if (n_rows_rank >= 3 && rows_per_band > 1) band_ty.push_back(ty0 + 1);
+  while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
   band_ty.push_back(ty1);
   const int n_bands = (int)band_ty.size() - 1;
   std::vector<cudaEvent_t> ev_in(n_bands), ev_done(n_bands);
