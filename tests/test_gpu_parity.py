@@ -517,3 +517,21 @@ def test_batch_256_equals_single_tiles_in_tensor_core_mode(fp16_engine):
         one = fp16_engine.run_tile(depth[i], dem[i])
         assert np.array_equal(batch["prediction_m"][i], one["prediction_m"]), i
         assert batch["dem_stats_used"][i] == one["dem_stats_used"]
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("FSR_BIG_TESTS"), reason="needs ~14 GB of host memory; set FSR_BIG_TESTS=1")
+def test_32k_raster_on_one_gpu_is_periodic_in_both_axes(fp16_engine):
+    """BASELINE config 5 (32768 x 32768, 7225 feather windows) through ONE engine: byte offsets beyond 2^32.  Inputs
+    repeat every 384 pixels along both axes, so interior window rows and columns must repeat bit for bit."""
+    n, period = 32768, 384
+    depth_p, dem_p = synth_raster(period, period, seed=33)
+    reps = -(-n // period)
+    dem = np.ascontiguousarray(np.tile(dem_p, (reps, reps))[:n, :n])
+    depth = np.ascontiguousarray(np.tile(depth_p, (reps, reps))[: n // 16, : n // 16])
+    out, n_tiles, _ = fp16_engine.run_raster(depth, dem)
+    assert n_tiles == 7225 and out.shape == (n, n)
+    ref = out[2 * period: 3 * period, 2 * period: 3 * period]
+    assert np.isfinite(ref).all() and ref.max() > 0.0
+    for ky in (3, 30, 57, 82):           # rows beyond 2^32 bytes into the raster from ky = 43 on
+        for kx in (2, 41, 83):
+            assert np.array_equal(out[ky * period: (ky + 1) * period, kx * period: (kx + 1) * period], ref), (ky, kx)
