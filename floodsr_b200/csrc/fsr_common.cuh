@@ -59,6 +59,14 @@ struct Profiler {
   std::vector<cudaEvent_t> pool;
   double ms[PROF_NCAT] = {0};
   long long count[PROF_NCAT] = {0};
+  // Consecutive LR convolution launches share ONE event pair: an event record between two kernels would cut the
+  // programmatic dependent launch edge between them.  The pair is closed by the next scope of any kind (or collect()).
+  long long open_idx = -1;
+  cudaStream_t open_s = nullptr;
+  void close_open() {
+    if (open_idx >= 0) cudaEventRecord(recs[(size_t)open_idx].b, open_s);
+    open_idx = -1;
+  }
   cudaEvent_t get() {
     if (!pool.empty()) {
       cudaEvent_t e = pool.back();
@@ -70,6 +78,7 @@ struct Profiler {
     return e;
   }
   void collect() {
+    close_open();
     for (auto& r : recs) {
       FSR_CUDA(cudaEventSynchronize(r.b));
       float t = 0.f;
@@ -94,15 +103,29 @@ struct ProfScope {
   Profiler* p;
   cudaStream_t s;
   size_t idx = 0;
+  bool deferred = false;  // the end event is recorded by the next scope (runs of LR convolutions)
   ProfScope(Profiler& prof, int cat, cudaStream_t stream) : p(prof.on ? &prof : nullptr), s(stream) {
     if (!p) return;
+    if (p->open_idx >= 0) {
+      if (cat == PROF_LR_CONV && p->recs[(size_t)p->open_idx].cat == cat && p->open_s == s) {
+        idx = (size_t)p->open_idx;
+        deferred = true;
+        return;
+      }
+      p->close_open();
+    }
     Profiler::Rec r{cat, p->get(), p->get()};
     FSR_CUDA(cudaEventRecord(r.a, s));
     p->recs.push_back(r);
     idx = p->recs.size() - 1;
+    if (cat == PROF_LR_CONV) {
+      p->open_idx = (long long)idx;
+      p->open_s = s;
+      deferred = true;
+    }
   }
   ~ProfScope() {
-    if (p) cudaEventRecord(p->recs[idx].b, s);
+    if (p && !deferred) cudaEventRecord(p->recs[idx].b, s);
   }
 };
 

@@ -25,6 +25,29 @@ constexpr int kConvPairs = 2;                           // M tiles one CTA of co
 template <int PAIR>
 constexpr int kConvThreads = 32 + 32 * PAIR + 128;  // producer warp, one MMA warp per M tile, 4 epilogue warps
 
+// Programmatic dependent launch: consecutive convolution layers are launched with the stream-serialisation attribute, so a
+// layer's CTAs may start (barrier set-up, TMEM allocation, constant weight loads) while the previous layer drains;
+// griddep_wait() returns once the previous kernel has completed and its writes are visible.  Nothing before the wait may
+// read activations or write global memory.  Both instructions are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t s, Args... args) {
+  static const bool off = getenv("FSR_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  FSR_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
 // MMA with the 64-bit shared-memory descriptors given as 32-bit halves: the issuing lane then only does 32-bit adds per
 // instruction (rebuilding 64-bit descriptors per MMA costs more issue time than a narrow MMA takes to execute)
 __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc) {
@@ -69,6 +92,7 @@ template <int BN, int PAIR>
 __global__ void __launch_bounds__(kConvThreads<PAIR>, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  griddep_launch_dependents();
   // stages are sized for this layer's K slice (kc 8-channel planes), so narrow layers fit several CTAs per SM and
   // their TMA latencies overlap.  With PAIR == 2 a CTA computes TWO M tiles (adjacent image blocks at the same
   // output position, so the same taps and weights): every weight slice fetched from L2 feeds two MMAs, one per
@@ -128,6 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // the previous layer's output (and the buffers it still reads) are safe from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -296,6 +321,7 @@ template <int BN>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  griddep_launch_dependents();
   const int plane_b = p.box_rows * p.pitch * 16;    // one 8-channel plane of a halo box
   const int box_bytes = p.kc * plane_b;
   const int stage_bytes = (box_bytes + 2 * p.pitch * 16 + 127) & ~127;  // slack: the last taps of padding positions read past the box
@@ -343,12 +369,16 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the packed weights are constants: their load may start before the previous layer has finished
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(w_full, (uint32_t)p.w_bytes);
+    bulk_load_1d(smem_w, p.wpack, (uint32_t)p.w_bytes, w_full);
+  }
+  griddep_wait();  // the previous layer's output (and the buffers it still reads) are safe from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)p.w_bytes);
-      bulk_load_1d(smem_w, p.wpack, (uint32_t)p.w_bytes, w_full);
       int s = 0;
       uint32_t ph = 1;
       long long st_wait = 0;
@@ -838,8 +868,8 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       attr = true;
     }
     p.stages = conv_stages<128>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) conv_tc_kernel<128, 2><<<grid, kConvThreads<2>, conv_smem_bytes<128>(kc, p.stages, 2), s>>>(m0, m1, p);
-    else conv_tc_kernel<128, 1><<<grid, kConvThreads<1>, conv_smem_bytes<128>(kc, p.stages, 1), s>>>(m0, m1, p);
+    if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<128, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc, p.stages, 1), s, m0, m1, p);
   } else if (BN == 64) {
     static bool attr = false;
     if (!attr) {
@@ -848,8 +878,8 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       attr = true;
     }
     p.stages = conv_stages<64>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) conv_tc_kernel<64, 2><<<grid, kConvThreads<2>, conv_smem_bytes<64>(kc, p.stages, 2), s>>>(m0, m1, p);
-    else conv_tc_kernel<64, 1><<<grid, kConvThreads<1>, conv_smem_bytes<64>(kc, p.stages, 1), s>>>(m0, m1, p);
+    if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<64, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc, p.stages, 1), s, m0, m1, p);
   } else {
     static bool attr = false;
     if (!attr) {
@@ -858,8 +888,8 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       attr = true;
     }
     p.stages = conv_stages<32>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) conv_tc_kernel<32, 2><<<grid, kConvThreads<2>, conv_smem_bytes<32>(kc, p.stages, 2), s>>>(m0, m1, p);
-    else conv_tc_kernel<32, 1><<<grid, kConvThreads<1>, conv_smem_bytes<32>(kc, p.stages, 1), s>>>(m0, m1, p);
+    if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<32, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc, p.stages, 1), s, m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
 }
@@ -918,10 +948,10 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   const int grid = p.n_mtiles < n_sms ? p.n_mtiles : n_sms;
   if (cout == 64) {
     FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    conv_rows_tc_kernel<64><<<grid, kRowsThreads, smem, s>>>(m0, m1, p);
+    launch_pdl(conv_rows_tc_kernel<64>, dim3((unsigned)grid), kRowsThreads, smem, s, m0, m1, p);
   } else {
     FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    conv_rows_tc_kernel<32><<<grid, kRowsThreads, smem, s>>>(m0, m1, p);
+    launch_pdl(conv_rows_tc_kernel<32>, dim3((unsigned)grid), kRowsThreads, smem, s, m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
   if (d_stats) {
