@@ -36,18 +36,44 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def _compile_one(args):
+    cmd, src = args
+    proc = subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
+    return src, proc.returncode, proc.stdout + proc.stderr, cmd
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every source to an object (in parallel, only the stale ones) and link the shared library."""
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in sources()] + ["-lcuda", "-o", str(LIB)]
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = find_nvcc()
+    obj_dir = PKG.parent / "build" / "obj"
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "floodsr_b200.h"]
+    h_time = max(h.stat().st_mtime for h in headers)
+    jobs, objs = [], []
+    for src in sources():
+        obj = obj_dir / (src.stem + ".o")
+        objs.append(obj)
+        if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, h_time):
+            cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-c", str(src), "-o", str(obj)]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            jobs.append((cmd, src))
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
+        for src, rc, out, cmd in pool.map(_compile_one, jobs):
+            if verbose or rc != 0:
+                sys.stderr.write(out)
+            if rc != 0:
+                raise RuntimeError(f"nvcc failed ({rc}): {' '.join(cmd)}")
+    cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", *[str(o) for o in objs], "-lcuda", "-o", str(LIB)]
     proc = subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
+        raise RuntimeError(f"nvcc link failed ({proc.returncode}): {' '.join(cmd)}")
     return LIB
 
 

@@ -34,7 +34,8 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_REQUIRE(hdr_.lr_tile > 0 && hdr_.hr_tile == hdr_.lr_tile * hdr_.scale, "inconsistent tile geometry");
   FSR_REQUIRE(hdr_.hr_tile % 64 == 0, "hr tile must be a multiple of 64");
   FSR_REQUIRE(hdr_.out_tensor >= 2 && hdr_.out_tensor < hdr_.n_tensors, "bad output tensor");
-  FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_BF16 || precision == FSR_PREC_FP16, "unknown precision mode");
+  FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_BF16 || precision == FSR_PREC_FP16 || precision == FSR_PREC_FP32_SIMT,
+              "unknown precision mode");
   if (const char* e = getenv("FSR_BAND_TILES")) band_tiles_ = std::max(1, atoi(e));
 
   const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
@@ -85,7 +86,7 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_CUDA(cudaMemset(d_flags_.p, 0, sizeof(unsigned)));
   tbuf_.resize(tensors_.size());
   tbase_.assign(tensors_.size(), nullptr);
-  if (precision_ != FSR_PREC_FP32) {
+  if (precision_ != FSR_PREC_FP32_SIMT) {
     cudaDeviceProp prop;
     FSR_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major != 10) throw Error(FSR_E_UNSUPPORTED, "the tensor-core backends need an sm_100 (Blackwell) device: tcgen05/TMEM/TMA");
@@ -104,6 +105,7 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
 Engine::~Engine() {
   cudaSetDevice(device_);
   for (auto& b : tbuf_) b.release();
+  for (auto& b : simt_buf_) b.release();
   for (DeviceBuf* b : {&d_weights_, &d_flags_, &d_headmid_, &d_dem_norm_, &d_depth_norm_, &d_pred_norm_, &d_dem_lr_, &d_tiles, &d_stats,
                        &d_in_depth, &d_in_dem, &d_out, &d_tmp_a, &d_tmp_b})
     b->release();
@@ -142,7 +144,7 @@ void Engine::ensure_arena(int n_tiles) {
   const int cap = std::min(ceil_div(n_tiles, 64) * 64, std::max(chunk_tiles_, n_tiles));  // grow-only, in steps of 64 tiles
   size_t headmid = 0;
   const size_t hr_px0 = (size_t)hdr_.hr_tile * hdr_.hr_tile, lr_px0 = (size_t)hdr_.lr_tile * hdr_.lr_tile;
-  if (precision_ != FSR_PREC_FP32) {
+  if (precision_ != FSR_PREC_FP32_SIMT) {
     tc_ensure_arena(cap);
     d_dem_norm_.ensure(hr_px0 * sizeof(float) * cap);
     d_pred_norm_.ensure(hr_px0 * sizeof(float) * cap);
@@ -239,7 +241,7 @@ void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_
       skip_op_ = pooled_op_;
     }
     float* pm = d_pred_m ? d_pred_m + (size_t)c0 * hr_px : nullptr;
-    if (precision_ != FSR_PREC_FP32) {
+    if (precision_ != FSR_PREC_FP32_SIMT) {
       tbase_[hdr_.out_tensor] = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
       tc_run_ops(false, n, 0, nullptr, max_depth, denom, s);
       tc_run_hr_phase(n, pm, max_depth, denom, s);

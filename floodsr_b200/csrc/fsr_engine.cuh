@@ -99,6 +99,7 @@ struct TcOp {
   bool pack_small = false;
   bool rows = false;       // runs the persistent row-box conv kernel
   int kc = 0, C0 = 0, C1 = 0;
+  float out_scale = 1.0f;  // split mode: inverse of the power-of-two factor carried by the packed weights
   std::vector<float> h_wdem, h_bias, h_w2;  // head epilogue constants (passed as kernel parameters)
   float h_b2 = 0.f;
 };
@@ -174,9 +175,13 @@ class Engine {
   void tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
   void tc_prepare_fused(const float* host_weights);
   void tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  void run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  int parts_ = 1;                       // 2: split fp16 (hi, lo) tensors and weights, three MMAs per product (FSR_PREC_FP32)
   int fused_ct_ = -1, fused_hd_ = -1;   // plan ops run by the fused high-resolution kernel, or -1
   DeviceBuf fused_hw_, fused_wt_;
-  std::vector<float> fused_bias_t_;
+  std::vector<float> fused_bias_t_, fused_bias_h_;
+  float fused_scale_t_inv_ = 1.f, fused_scale_h_inv_ = 1.f;
+  std::vector<DeviceBuf> simt_buf_;     // fp32 NHWC tensors of the SIMT high-resolution pair (split mode without the fused kernel)
   // convT / head overlap across sub-chunks (tc_run_hr_phase)
   bool hr_overlap_ = true;
   int head_sms_ = 96;

@@ -1,10 +1,14 @@
-// FSR_PREC_BF16 backend of the Engine: tensor formats, weight packing and op dispatch onto the tcgen05 kernels.
+// Tensor-core backend of the Engine (every precision mode but the SIMT diagnostic one): tensor formats, weight packing and
+// op dispatch onto the tcgen05 kernels.  FSR_PREC_BF16 / FSR_PREC_FP16 store activations and weights as one 16-bit tensor;
+// FSR_PREC_FP32 (the <= 1e-4 m mode) stores every one of them as a split fp16 pair (hi, lo) and runs three MMAs per product
+// (tc_common.cuh: "parts" == 2).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 
 #include "fsr_engine.cuh"
@@ -16,22 +20,22 @@ int conv_tc_bn(int cout);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
-                    cudaStream_t s);
-bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc);
+                    int parts, float out_scale, int cpad_out, cudaStream_t s);
+bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc, int parts);
 void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                          const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                          long long plane_out, int n_img, int H, int W, int cout, int act, float alpha, int half, int n_sms,
-                         cudaStream_t s);
+                         int parts, float out_scale, cudaStream_t s);
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
-                       int chunks, int half, cudaStream_t s);
+                       int chunks, int half, int parts, cudaStream_t s);
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, int half, int im_in, int im_out, cudaStream_t s);
+                     long long plane_in, long long plane_out, int half, int im_in, int im_out, int parts, cudaStream_t s);
 void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
                          long long plane_in, long long plane_out, int im_in, int im_out, cudaStream_t s);
 void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
-                        int half, cudaStream_t s);
+                        int half, long long lo_vec, cudaStream_t s);
 void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, long long plane, int C, int half, int im,
-                        cudaStream_t s);
+                        long long lo_off, cudaStream_t s);
 void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bfloat16* wpack, const float* bias,
                      __nv_bfloat16* dst, long long plane_out, int n_img, int Hin, int Win, int cin, int cout, int k, int act,
                      float alpha, int half, cudaStream_t s);
@@ -50,6 +54,17 @@ void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_
                         float alpha_t, const __nv_bfloat16* hw_pack, const float* w2, const float* b2, int act_h, float alpha_h,
                         const float* dem, float* pred_m, float* pred_norm, int n_img, int H, float max_depth, float denom,
                         int half, int n_sms, cudaStream_t s);
+
+// split-operand (fp32-tolerance) variant of the fused kernel: k_tc_fused_x3.cu
+bool fused_x3_ok(int H, int W, int lr_h, int lr_w, int cin_t, int cout_t, int k_t, int cmid, int ksz);
+size_t fused_x3_hw_elems();
+size_t fused_x3_wt_elems();
+void fused_x3_pack_head(const float* w, float scale, uint16_t* dst);
+void fused_x3_pack_convt(const float* w, float scale, uint16_t* dst);
+void launch_fused_x3(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfloat16* wt_pack, const float* bias_t, float scale_t_inv,
+                     int act_t, float alpha_t, const __nv_bfloat16* hw_pack, const float* bias_h, float scale_h_inv, const float* w2,
+                     const float* b2, int act_h, float alpha_h, const float* dem, float* pred_m, float* pred_norm, int n_img, int H,
+                     float max_depth, float denom, int n_sms, cudaStream_t s);
 
 static bool g_pack_half = false;  // 16-bit format used while packing weights (set by tc_prepare)
 static inline uint16_t f2bf(float f) {
@@ -77,9 +92,37 @@ static inline float bf2f(uint16_t u) {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// Split mode: weights are multiplied by a power of two so that the largest one lands in [2^9, 2^10): the lo parts of all
+// but vanishing weights are then normal fp16 numbers.  The kernels' epilogues multiply by the inverse (exact).
+float split_weight_scale(const float* w, size_t n) {
+  float m = 0.f;
+  for (size_t i = 0; i < n; ++i) m = std::max(m, std::fabs(w[i]));
+  if (!(m > 0.f) || !std::isfinite(m)) return 1.0f;
+  int e = 0;
+  std::frexp(m, &e);  // m = f * 2^e, f in [0.5, 1)
+  return std::ldexp(1.0f, 10 - e);
+}
+static inline uint16_t f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+static inline float h2f(uint16_t u) {
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+// (hi, lo) fp16 pair of a scaled weight
+void split_weight(float v, uint16_t& hi, uint16_t& lo) {
+  hi = f2h(v);
+  lo = f2h(v - h2f(hi));
+}
+
 // Decide per-tensor storage and pack every conv-like op's weights into the layouts the kernels stream.
 void Engine::tc_prepare(const float* w) {
-  g_pack_half = precision_ == FSR_PREC_FP16;
+  parts_ = precision_ == FSR_PREC_FP32 ? 2 : 1;
+  g_pack_half = precision_ != FSR_PREC_BF16;
   const int nt = (int)tensors_.size();
   tc_fmt_.assign(nt, 0);
   tc_cpad_.assign(nt, 0);
@@ -118,7 +161,8 @@ void Engine::tc_prepare(const float* w) {
       need_cp8(op.res, "conv residual");
       FSR_REQUIRE(op.cout % 32 == 0, "bf16 backend: conv output channels must be a multiple of 32");
       int kc = std::gcd(C0 / 8, C1 ? C1 / 8 : C0 / 8);
-      while (kc > 8 || (kc % 2)) {
+      const int kc_max = parts_ == 2 ? 4 : 8;  // split stages carry two parts: same bytes per stage
+      while (kc > kc_max || (kc % 2)) {
         if (kc % 2) throw Error(FSR_E_UNSUPPORTED, "bf16 backend: conv input channels must be multiples of 16");
         kc /= 2;
       }
@@ -126,7 +170,7 @@ void Engine::tc_prepare(const float* w) {
         // wide, shallow levels run the persistent row-box kernel, which works on 32-channel groups
         const auto& d = tensors_[op.dst];
         const int kc_rows = kc > 4 ? 4 : kc;
-        if (!getenv("FSR_NO_CONV_ROWS") && !tc_im_[op.dst] && conv_rows_ok(d.h, d.w, op.k, op.cout, C0, C1, kc_rows)) {
+        if (!getenv("FSR_NO_CONV_ROWS") && !tc_im_[op.dst] && conv_rows_ok(d.h, d.w, op.k, op.cout, C0, C1, kc_rows, parts_)) {
           kc = kc_rows;
           t.rows = true;
         }
@@ -141,15 +185,21 @@ void Engine::tc_prepare(const float* w) {
       const int real_c0 = t.pack_small ? tensors_[op.src0].c + (op.src1 >= 0 ? tensors_[op.src1].c : 0) : tensors_[op.src0].c;
       const int real_c1 = t.pack_small ? 0 : (op.src1 >= 0 ? tensors_[op.src1].c : 0);
       const int cin_real = real_c0 + real_c1;
-      std::vector<uint16_t> pk((size_t)n_tiles * taps * (s0 + s1) * kc * BN * 8, 0);
+      std::vector<uint16_t> pk((size_t)parts_ * n_tiles * taps * (s0 + s1) * kc * BN * 8, 0);
       const float* wt = w + op.w_off;  // [tap][cin_real][cout]
-      size_t pos = 0;
+      const float wscale = parts_ == 2 ? split_weight_scale(wt, (size_t)taps * cin_real * op.cout) : 1.0f;
+      t.out_scale = 1.0f / wscale;
+      // element strides of the packed layout: conv_tc_kernel streams [n_tile][tap][stage][part][kc][BN][8], the row-box kernel
+      // keeps [part][tap][group][kc][BN][8] resident (one output tile)
+      const size_t slice = (size_t)kc * BN * 8;
+      const size_t part_stride = t.rows ? (size_t)taps * (s0 + s1) * slice : slice;
+      const size_t stage_stride = t.rows ? slice : (size_t)parts_ * slice;
       for (int nt_i = 0; nt_i < n_tiles; ++nt_i)
         for (int tap = 0; tap < taps; ++tap)
           for (int st = 0; st < s0 + s1; ++st)
             for (int j = 0; j < kc; ++j)
               for (int n = 0; n < BN; ++n)
-                for (int e = 0; e < 8; ++e, ++pos) {
+                for (int e = 0; e < 8; ++e) {
                   const int co = nt_i * BN + n;
                   int ci;  // index into the concatenated real input channels, -1 = padding
                   if (st < s0) {
@@ -159,10 +209,17 @@ void Engine::tc_prepare(const float* w) {
                     const int c = ((st - s0) * kc + j) * 8 + e;
                     ci = c < real_c1 ? real_c0 + c : -1;
                   }
-                  if (ci >= 0 && co < op.cout) pk[pos] = f2bf(wt[((size_t)tap * cin_real + ci) * op.cout + co]);
+                  if (ci < 0 || co >= op.cout) continue;
+                  const size_t pos = (((size_t)nt_i * taps + tap) * (s0 + s1) + st) * stage_stride + ((size_t)j * BN + n) * 8 + e;
+                  const float v = wt[((size_t)tap * cin_real + ci) * op.cout + co];
+                  if (parts_ == 2) split_weight(v * wscale, pk[pos], pk[pos + part_stride]);
+                  else pk[pos] = f2bf(v);
                 }
       t.wpack.ensure(pk.size() * 2);
       FSR_CUDA(cudaMemcpy(t.wpack.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else if (parts_ == 2 && (op.kind == FSR_OP_CONVT || op.kind == FSR_OP_HEAD)) {
+      // split mode: the high-resolution end runs in the fused split kernel (tc_prepare_fused)
+      if (op.kind == FSR_OP_CONVT) need_cp8(op.src0, "convT source");
     } else if (op.kind == FSR_OP_CONVT) {
       need_cp8(op.src0, "convT source");
       need_cp8(op.dst, "convT output");
@@ -230,6 +287,32 @@ void Engine::tc_prepare_fused(const float* w) {
   const auto& tl = tensors_[ct.src0];
   const auto& tf = tensors_[ct.dst];
   if (!tc_fmt_[ct.src0] || tc_cpad_[ct.src0] != 32) return;
+  if (parts_ == 2) {
+    if (getenv("FSR_X3_HR_SIMT") || !fused_x3_ok(tf.h, tf.w, tl.h, tl.w, tl.c, ct.cout, ct.k, hd.cout, hd.k)) return;
+    const float* wh = w + hd.w_off;  // [3][3][33][32]
+    const float* wc = w + ct.w_off;  // [16][16][32][32]
+    const float sh = split_weight_scale(wh, (size_t)hd.k * hd.k * (tf.c + 1) * hd.cout);
+    const float st = split_weight_scale(wc, (size_t)ct.k * ct.k * tl.c * ct.cout);
+    std::vector<uint16_t> hw(fused_x3_hw_elems(), 0), wt(fused_x3_wt_elems(), 0);
+    fused_x3_pack_head(wh, sh, hw.data());
+    fused_x3_pack_convt(wc, st, wt.data());
+    fused_hw_.ensure(hw.size() * 2);
+    fused_wt_.ensure(wt.size() * 2);
+    FSR_CUDA(cudaMemcpy(fused_hw_.p, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+    FSR_CUDA(cudaMemcpy(fused_wt_.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+    fused_bias_t_.assign(ct.cout, 0.f);
+    if (ct.b_off >= 0) std::copy(w + ct.b_off, w + ct.b_off + ct.cout, fused_bias_t_.begin());
+    fused_bias_h_.assign(hd.cout, 0.f);
+    if (hd.b_off >= 0) std::copy(w + hd.b_off, w + hd.b_off + hd.cout, fused_bias_h_.begin());
+    fused_scale_t_inv_ = 1.0f / st;
+    fused_scale_h_inv_ = 1.0f / sh;
+    TcOp& th = tc_ops_[hr_ops[1]];
+    th.h_w2.assign(w + hd.w2_off, w + hd.w2_off + hd.cout);
+    th.h_b2 = hd.b2_off >= 0 ? w[hd.b2_off] : 0.f;
+    fused_ct_ = hr_ops[0];
+    fused_hd_ = hr_ops[1];
+    return;
+  }
   if (!fused_hr_ok(tf.h, tf.w, tl.h, tl.w, tl.c, ct.cout, ct.k, hd.cout, hd.k)) return;
   std::vector<uint16_t> hw(fused_hw_elems(), 0), wt(fused_wt_elems(), 0);
   fused_pack_head(w + hd.w_off, hd.b_off >= 0 ? w + hd.b_off : nullptr, hw.data(), f2bf, bf2f);
@@ -249,7 +332,7 @@ void Engine::tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, 
   const fsr_op& hd = ops_[fused_hd_];
   const TcOp& th = tc_ops_[fused_hd_];
   const auto& tf = tensors_[ct.dst];
-  const int half = precision_ == FSR_PREC_FP16 ? 1 : 0;
+  const int half = precision_ != FSR_PREC_BF16 ? 1 : 0;
   float* pn = tbase_[hd.dst];  // may be nullptr when the caller does not want the normalised prediction
   float* pm = d_pred_m;
   if (!pm) {
@@ -257,6 +340,12 @@ void Engine::tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, 
     pm = d_tmp_b.as<float>();
   }
   ProfScope scope(prof, PROF_HEAD, s);
+  if (parts_ == 2) {
+    launch_fused_x3(reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]), tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(),
+                    fused_bias_t_.data(), fused_scale_t_inv_, ct.act, ct.alpha, fused_hw_.as<__nv_bfloat16>(), fused_bias_h_.data(),
+                    fused_scale_h_inv_, th.h_w2.data(), &th.h_b2, hd.act, hd.alpha, tbase_[1], pm, pn, n, tf.h, max_depth, denom, n_sms_, s);
+    return;
+  }
   launch_fused_hr_tc(reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]), tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(),
                      fused_bias_t_.data(), ct.act, ct.alpha, fused_hw_.as<__nv_bfloat16>(), th.h_w2.data(), &th.h_b2, hd.act, hd.alpha,
                      tbase_[1], pm, pn, n, tf.h, max_depth, denom, half, n_sms_, s);
@@ -268,13 +357,14 @@ void Engine::tc_ensure_arena(int cap) {
     if (fused_ct_ >= 0 && (int)i == ops_[fused_ct_].dst) continue;  // the feature map stays on chip
     const auto& t = tensors_[i];
     const size_t tiles = big_[i] ? hr_sub_ : cap;
-    const size_t elt = tc_fmt_[i] ? 2 : 4;
+    const size_t elt = tc_fmt_[i] ? 2 * parts_ : 4;  // split tensors: hi tensor + lo tensor
+    if (parts_ == 2 && big_[i] && tc_fmt_[i]) continue;  // split mode never streams a 16-bit HR feature map through HBM
     tbuf_[i].ensure((size_t)t.h * t.w * tc_cpad_[i] * elt * tiles);
   }
   for (size_t oi = 0; oi < ops_.size(); ++oi)
     if (tc_ops_[oi].pack_small) {
       const auto& d = tensors_[ops_[oi].dst];
-      tc_ops_[oi].packbuf.ensure((size_t)d.h * d.w * 16 * 2 * cap);
+      tc_ops_[oi].packbuf.ensure((size_t)d.h * d.w * 16 * 2 * parts_ * cap);
     }
 }
 
@@ -298,6 +388,10 @@ void Engine::tc_run_ops(bool hr_phase, int n, int sub_start, float* d_pred_m, fl
 void Engine::tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
   if (fused_ct_ >= 0 && skip_op_ != fused_ct_ && skip_op_ != fused_hd_) {
     tc_run_fused(n, d_pred_m, max_depth, denom, s);
+    return;
+  }
+  if (parts_ == 2) {
+    run_hr_simt(n, d_pred_m, max_depth, denom, s);
     return;
   }
   std::vector<int> hr_ops;
@@ -338,9 +432,51 @@ void Engine::tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float deno
   tbase_[ftid] = bufs[0];
 }
 
+// Split mode, high-resolution layers the fused split kernel does not cover (or FSR_X3_HR_SIMT=1, the A/B switch of the parity
+// tests): the low-resolution result is converted to fp32 NHWC and the layers run as plain fp32 FMA kernels (k_fp32.cu), a few
+// tiles at a time.  Correct for every graph the lowering accepts, far from the tensor-core roofline.
+void Engine::run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
+  const int sub_tiles = 4;
+  simt_buf_.resize(tensors_.size());
+  std::vector<float*> saved = tbase_;
+  const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
+  size_t headmid = 0;
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    if (!op_hr_[i] || (int)i == skip_op_) continue;
+    const fsr_op& op = ops_[i];
+    for (int tid : {op.src0, op.src1, op.res}) {
+      if (tid < 0 || big_[tid] || !tc_fmt_[tid] || tbase_[tid] != saved[tid]) continue;
+      const auto& t = tensors_[tid];  // low-resolution CP8 pair -> fp32 NHWC
+      simt_buf_[tid].ensure((size_t)cap_tiles_ * t.h * t.w * t.c * sizeof(float));
+      ProfScope scope(prof, PROF_LR_MISC, s);
+      launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(saved[tid]), simt_buf_[tid].as<float>(), n, t.h, t.w, tc_plane(tid), t.c, 1,
+                         tc_im_[tid], (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8, s);
+      tbase_[tid] = simt_buf_[tid].as<float>();
+    }
+    if (big_[op.dst] && (int)op.dst != hdr_.out_tensor) {
+      const auto& t = tensors_[op.dst];
+      simt_buf_[op.dst].ensure((size_t)sub_tiles * t.h * t.w * t.c * sizeof(float));
+      tbase_[op.dst] = simt_buf_[op.dst].as<float>();
+    }
+    if (op.kind == FSR_OP_HEAD) headmid = std::max(headmid, hr_px * op.cout * sizeof(float) * sub_tiles);
+  }
+  if (headmid) d_headmid_.ensure(headmid);
+  float* pn = tbase_[hdr_.out_tensor] ? tbase_[hdr_.out_tensor] : d_pred_norm_.as<float>();
+  tbase_[hdr_.out_tensor] = pn;
+  for (int sub = 0; sub < n; sub += sub_tiles) run_ops(true, std::min(sub_tiles, n - sub), sub, s);
+  if (d_pred_m) {
+    ProfScope scope(prof, PROF_INVERT, s);
+    launch_invert_depth(pn, d_pred_m, (size_t)n * hr_px, max_depth, denom, s);
+  }
+  tbase_ = saved;
+}
+
 void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int head_sms) {
   const float* W = d_weights_.as<float>();
-  const int half = precision_ == FSR_PREC_FP16 ? 1 : 0;
+  const int half = precision_ != FSR_PREC_BF16 ? 1 : 0;
+  const int parts = parts_;
+  // elements between the hi and the lo tensor of a split CP8 tensor
+  auto lo_off = [&](int tid) -> long long { return parts == 2 ? (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8 : 0; };
   auto wp = [&](int off) -> const float* { return off >= 0 ? W + off : nullptr; };
   // element pointer of a tensor for the live sub-batch: CP8 planes keep their capacity stride, so the sub-batch
   // offset is a pixel offset inside every plane
@@ -372,7 +508,7 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
           __nv_bfloat16* pb = tc.packbuf.as<__nv_bfloat16>() + (size_t)sub_start * td.h * td.w * 8;
           const long long plane = (long long)cap_tiles_ * td.h * td.w;
           launch_pack_small(f32(op.src0), ts.c, f32(op.src1), op.src1 >= 0 ? tensors_[op.src1].c : 0, pb, (long long)n * td.h * td.w,
-                            plane, 2, half, s);
+                            plane, 2, half, parts, s);
           s0 = pb;
           pl0 = plane;
         } else {
@@ -385,21 +521,23 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
         }
         if (tc.rows)
           launch_conv_rows_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res),
-                              cp8(op.dst), tc_plane(op.dst), n, td.h, td.w, op.cout, op.act, op.alpha, half, n_sms_, s);
+                              cp8(op.dst), tc_plane(op.dst), n, td.h, td.w, op.cout, op.act, op.alpha, half, n_sms_, parts, tc.out_scale, s);
         else
           launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
-                         tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, tc_im_[op.dst], s);
+                         tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, tc_im_[op.dst], parts, tc.out_scale,
+                         tc_cpad_[op.dst], s);
         break;
       }
       case FSR_OP_POOL:
         if (tc_fmt_[op.src0])
           launch_pool_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, op.mode, tc_plane(op.src0),
-                          tc_plane(op.dst), half, tc_im_[op.src0], tc_im_[op.dst], s);
+                          tc_plane(op.dst), half, tc_im_[op.src0], tc_im_[op.dst], parts, s);
         else
           launch_pool_fp32(f32(op.src0), f32(op.dst), n, ts.h, ts.w, ts.c, op.k, op.mode, s);
         break;
       case FSR_OP_UPSAMPLE:
-        launch_upsample_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst),
+        // a pure copy: the lo tensor of a split source is simply more planes
+        launch_upsample_cp8(cp8(op.src0), cp8(op.dst), parts * tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst),
                             tc_im_[op.src0], tc_im_[op.dst], s);
         break;
       case FSR_OP_ELTWISE: {
@@ -408,15 +546,18 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
         const long long live = tc_im_[op.dst] ? tc_plane(op.dst) : (long long)n * td.h * td.w;
         for (int c8 = 0; c8 < tc_cpad_[op.dst] / 8; ++c8) {
           const size_t o = (size_t)c8 * tc_plane(op.dst) * 8;
-          launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, half, s);
+          launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, half,
+                             lo_off(op.dst) / 8, s);
         }
         break;
       }
       case FSR_OP_CONVT:
+        if (parts == 2) throw Error(FSR_E_UNSUPPORTED, "split mode runs the high-resolution end in the fused kernel or the fp32 pair");
         launch_convt_tc(cp8(op.src0), tc_plane(op.src0), tc.wpack.as<__nv_bfloat16>(), wp(op.b_off), cp8(op.dst), tc_plane(op.dst), n,
                         ts.h, ts.w, tc_cpad_[op.src0], op.cout, op.k, op.act, op.alpha, half, s);
         break;
       case FSR_OP_HEAD: {
+        if (parts == 2) throw Error(FSR_E_UNSUPPORTED, "split mode runs the high-resolution end in the fused kernel or the fp32 pair");
         float* pn = f32(op.dst);  // may be nullptr when the caller does not want the normalised prediction
         float* pm = d_pred_m ? d_pred_m + (size_t)sub_start * td.h * td.w : nullptr;
         if (!pm) {
@@ -438,9 +579,9 @@ void Engine::debug_read_tensor(int tid, int n_tiles, float* d_out, cudaStream_t 
   FSR_REQUIRE(tid >= 0 && tid < (int)tensors_.size() && tbase_[tid], "tensor is not materialised");
   const auto& t = tensors_[tid];
   const long long n_pix = (long long)n_tiles * t.h * t.w;
-  if (precision_ != FSR_PREC_FP32 && tc_fmt_[tid]) {
+  if (precision_ != FSR_PREC_FP32_SIMT && tc_fmt_[tid]) {
     launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(tbase_[tid]), d_out, n_tiles, t.h, t.w, tc_plane(tid), t.c,
-                       precision_ == FSR_PREC_FP16 ? 1 : 0, tc_im_[tid], s);
+                       precision_ != FSR_PREC_BF16 ? 1 : 0, tc_im_[tid], parts_ == 2 ? (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8 : 0, s);
   } else {
     FSR_CUDA(cudaMemcpyAsync(d_out, tbase_[tid], (size_t)n_pix * t.c * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }

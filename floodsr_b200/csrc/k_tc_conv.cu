@@ -81,8 +81,11 @@ struct ConvTcParams {
   int im;                  // 1: image-major tensors ("IM8" [C/8][H*W][N][8], maps of <= 64 pixels): an M tile is 128 images at
                            // one output pixel, each tap is ONE contiguous 2 KB run per channel chunk, out-of-range taps are skipped
   int ncap;                // images per pixel plane of IM8 tensors (allocation capacity)
+  int parts;               // 1: plain 16-bit operands; 2: split fp16 (hi, lo) operands, three MMAs per product (tc_common.cuh)
+  float out_scale;         // parts == 2: the packed weights carry a power-of-two factor, undone here
+  long long lo_off;        // parts == 2: elements between the hi and the lo tensor of out / res
   long long plane;         // pixels per CP8 plane of the output/residual tensors (N_capacity * H * W)
-  const __nv_bfloat16* wpack;  // [n_tile][tap][stage][kc][BN][8]
+  const __nv_bfloat16* wpack;  // [n_tile][tap][stage][part][kc][BN][8]
   const float* bias;           // [cout] or nullptr
   const __nv_bfloat16* res;    // CP8 residual or nullptr
   __nv_bfloat16* out;          // CP8 output
@@ -97,8 +100,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // their TMA latencies overlap.  With PAIR == 2 a CTA computes TWO M tiles (adjacent image blocks at the same
   // output position, so the same taps and weights): every weight slice fetched from L2 feeds two MMAs, one per
   // accumulator, each issued by its own warp.
-  const int kABytesMax = p.kc * 128 * 16;
-  const int kBBytesMax = p.kc * BN * 16;
+  const int kABytesMax = p.parts * p.kc * 128 * 16;
+  const int kBBytesMax = p.parts * p.kc * BN * 16;
   const int a_stage = PAIR * kABytesMax;
   uint8_t* smem_a = smem_raw;                                   // p.stages x pair x a_bytes
   uint8_t* smem_b = smem_raw + p.stages * a_stage;                // p.stages x b_bytes
@@ -111,8 +114,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.ksz * p.ksz;
   const int stages_per_tap = p.s0 + p.s1;
-  const uint32_t a_bytes = (uint32_t)p.kc * 128u * 16u;
-  const uint32_t b_bytes = (uint32_t)p.kc * BN * 16u;
+  const uint32_t a_bytes = (uint32_t)kABytesMax;  // one TMA box: [part][kc][128 px][16 B]
+  const uint32_t b_bytes = (uint32_t)kBBytesMax;
 
   // tile coordinates (IM8: tx = output pixel x, ty = output pixel y, tn = tile of 128 images)
   int t = blockIdx.x;
@@ -175,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (p.im) tma_load_5d(dst, tm, &full[s], (tn0 + h) * 256, (ty + dy) * p.W + tx + dx, chunk0, 0, 0);
             else tma_load_5d(dst, tm, &full[s], 2 * (tx * p.bw + dx), ty * p.bh + dy, (tn0 + h) * p.bn, chunk0, 0);
           }
-          const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)p.kc * BN * 8);
+          const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)p.parts * p.kc * BN * 8);
           bulk_load_1d(smem_b + s * kBBytesMax, wsrc, b_bytes, &full[s]);
         }
       }
@@ -190,6 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t a_step = (uint32_t)a_stage >> 4, b_step = (uint32_t)kBBytesMax >> 4;
       const uint32_t d = tmem_base + h * BN;
       const int kpairs = p.kc / 2;
+      const uint32_t a_part = (uint32_t)(p.kc * 128 * 16) >> 4, b_part = (uint32_t)(p.kc * BN * 16) >> 4;
       const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0;
@@ -198,8 +202,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         if (leader) {
           // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
-          for (int j = 0; j < kpairs; ++j)
-            umma_lo(d, a_lo + j * ((2 * 128 * 16) >> 4), b_lo + j * ((2 * BN * 16) >> 4), kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+          for (int j = 0; j < kpairs; ++j) {
+            const uint32_t aj = a_lo + j * ((2 * 128 * 16) >> 4), bj = b_lo + j * ((2 * BN * 16) >> 4);
+            umma_lo(d, aj, bj, kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+            if (p.parts == 2) {  // + a_lo * b_hi + a_hi * b_lo
+              umma_lo(d, aj + a_part, bj, kDescHi, idesc, 1u);
+              umma_lo(d, aj, bj + b_part, kDescHi, idesc, 1u);
+            }
+          }
           umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
           if (it == n_iters_cta - 1) umma_commit(accum_full);
         }
@@ -224,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                  : ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
       // the first tile's residual is fetched while the MMAs still run
       uint4 resv[BN / 8];
-      if (p.res && valid) {
+      if (p.res && valid && p.parts == 1) {
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c) {
           const int co = n_tile * BN + c * 8;
@@ -244,6 +254,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int co = n_tile * BN + c * 8;
         if (valid && co < p.cout) {
           const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
+          if (p.parts == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
+          }
           if (p.bias) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
@@ -252,7 +266,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if (p.res) {
             float r[8];
-            unpack_x8(resv[c], r, p.half);
+            if (p.parts == 2)
+              join_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), __ldg(reinterpret_cast<const uint4*>(p.res + p.lo_off + off)), r);
+            else
+              unpack_x8(resv[c], r, p.half);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += r[i];
           }
@@ -263,7 +280,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * p.alpha;
           }
-          *reinterpret_cast<uint4*>(p.out + off) = pack_x8(v, p.half);
+          if (p.parts == 2) {
+            uint4 hi, lo;
+            split_x8(v, hi, lo);
+            *reinterpret_cast<uint4*>(p.out + off) = hi;
+            *reinterpret_cast<uint4*>(p.out + p.lo_off + off) = lo;
+          } else {
+            *reinterpret_cast<uint4*>(p.out + off) = pack_x8(v, p.half);
+          }
         }
       }
     }
@@ -308,9 +332,12 @@ struct ConvRowsParams {
   float alpha;
   int half;
   int stages;          // halo-box ring depth (as many as fit beside the weights)
+  int parts;           // 1: plain 16-bit operands; 2: split fp16 (hi, lo) operands, three MMAs per product
+  float out_scale;     // parts == 2: power-of-two factor carried by the packed weights, undone in the epilogue
+  long long lo_off;    // parts == 2: elements between the hi and the lo tensor of out / res
   unsigned long long* stats;  // FSR_ROWS_STATS: per-CTA clock totals of the pipeline roles (diagnostics)
   long long plane;     // pixels per CP8 plane of the output/residual tensors
-  const __nv_bfloat16* wpack;  // [tap][group][kc][BN][8]
+  const __nv_bfloat16* wpack;  // [part][tap][group][kc][BN][8]
   int w_bytes;
   const float* bias;
   const __nv_bfloat16* res;
@@ -323,7 +350,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   griddep_launch_dependents();
   const int plane_b = p.box_rows * p.pitch * 16;    // one 8-channel plane of a halo box
-  const int box_bytes = p.kc * plane_b;
+  const int box_bytes = p.parts * p.kc * plane_b;   // [part][kc][box_rows * pitch px][16 B], one TMA box
   const int stage_bytes = (box_bytes + 2 * p.pitch * 16 + 127) & ~127;  // slack: the last taps of padding positions read past the box
   const int w_round = (p.w_bytes + 1023) & ~1023;
   uint8_t* smem_w = smem_raw;
@@ -419,6 +446,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t st_u = (uint32_t)stage_bytes >> 4, row_u = (uint32_t)p.pitch;  // stage / image-row strides in 16-byte units
     const uint32_t kpl_u = (uint32_t)(2 * plane_b) >> 4;                            // one MMA = two channel planes
     const uint32_t wtap_u = (uint32_t)(groups * p.kc * BN * 16) >> 4, wgrp_u = (uint32_t)(p.kc * BN * 16) >> 4;
+    const uint32_t a_part = (uint32_t)(p.kc * plane_b) >> 4, w_part = 9u * wtap_u;  // hi -> lo operand distances
     const int kpairs = p.kc / 2;
     const bool leader = elect_one();
     int nt = e;
@@ -450,6 +478,14 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const uint32_t b_t = b_g + tap * wtap_u;
             umma_lo(d, a_t, b_t, kDescHi, idesc, (g > 0 || tap > 0) ? 1u : 0u);
             if (kpairs > 1) umma_lo(d, a_t + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
+            if (p.parts == 2) {  // + a_lo * w_hi + a_hi * w_lo
+              umma_lo(d, a_t + a_part, b_t, kDescHi, idesc, 1u);
+              umma_lo(d, a_t, b_t + w_part, kDescHi, idesc, 1u);
+              if (kpairs > 1) {
+                umma_lo(d, a_t + a_part + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
+                umma_lo(d, a_t + kpl_u, b_t + w_part + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
+              }
+            }
           }
           umma_commit(&empty[s]);
           if (g == groups - 1) umma_commit(&acc_full[ab]);
@@ -490,7 +526,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const bool valid = x < p.W && y < p.H;   // padding positions are dropped
       const long long pix = ((long long)img * p.H + y) * p.W + x;
       uint4 resv[BN / 8];  // fetched while the tile's MMAs still run
-      if (p.res && valid) {
+      if (p.res && valid && p.parts == 1) {
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)c * p.plane + pix) * 8));
       }
@@ -519,12 +555,16 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             float o[8];
             {
               const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co), b1 = *reinterpret_cast<const float4*>(s_bias + co + 4);
-              o[0] = v[c * 8] + b0.x; o[1] = v[c * 8 + 1] + b0.y; o[2] = v[c * 8 + 2] + b0.z; o[3] = v[c * 8 + 3] + b0.w;
-              o[4] = v[c * 8 + 4] + b1.x; o[5] = v[c * 8 + 5] + b1.y; o[6] = v[c * 8 + 6] + b1.z; o[7] = v[c * 8 + 7] + b1.w;
+              const float sc = p.out_scale;  // 1 unless parts == 2
+              o[0] = fmaf(v[c * 8], sc, b0.x); o[1] = fmaf(v[c * 8 + 1], sc, b0.y); o[2] = fmaf(v[c * 8 + 2], sc, b0.z); o[3] = fmaf(v[c * 8 + 3], sc, b0.w);
+              o[4] = fmaf(v[c * 8 + 4], sc, b1.x); o[5] = fmaf(v[c * 8 + 5], sc, b1.y); o[6] = fmaf(v[c * 8 + 6], sc, b1.z); o[7] = fmaf(v[c * 8 + 7], sc, b1.w);
             }
             if (p.res) {
               float r[8];
-              unpack_x8(resv[c32 * 4 + c], r, p.half);
+              if (p.parts == 2)
+                join_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), __ldg(reinterpret_cast<const uint4*>(p.res + p.lo_off + off)), r);
+              else
+                unpack_x8(resv[c32 * 4 + c], r, p.half);
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] += r[i];
             }
@@ -535,7 +575,14 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.0f ? o[i] : o[i] * p.alpha;
             }
-            *reinterpret_cast<uint4*>(p.out + off) = pack_x8(o, p.half);
+            if (p.parts == 2) {
+              uint4 hi, lo;
+              split_x8(o, hi, lo);
+              *reinterpret_cast<uint4*>(p.out + off) = hi;
+              *reinterpret_cast<uint4*>(p.out + p.lo_off + off) = lo;
+            } else {
+              *reinterpret_cast<uint4*>(p.out + off) = pack_x8(o, p.half);
+            }
           }
         }
       }
@@ -560,7 +607,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
 // concat of up to two 1-channel fp32 NHWC tensors -> CP8 bf16 with `chunks` 8-channel planes (zero padded)
 __global__ void pack_small_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
-                                  __nv_bfloat16* __restrict__ dst, long long n_pix, long long plane, int chunks, int half) {
+                                  __nv_bfloat16* __restrict__ dst, long long n_pix, long long plane, int chunks, int half, int parts) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * chunks; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i % n_pix;
     const int ch = (int)(i / n_pix);
@@ -573,7 +620,14 @@ __global__ void pack_small_kernel(const float* __restrict__ s0, int c0, const fl
       else if (c < c0 + c1) x = __ldg(s1 + pix * c1 + (c - c0));
       v[k] = x;
     }
-    *reinterpret_cast<uint4*>(dst + ((long long)ch * plane + pix) * 8) = pack_x8(v, half);
+    if (parts == 2) {
+      uint4 hi, lo;
+      split_x8(v, hi, lo);
+      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane + pix) * 8) = hi;
+      *reinterpret_cast<uint4*>(dst + ((long long)(chunks + ch) * plane + pix) * 8) = lo;
+    } else {
+      *reinterpret_cast<uint4*>(dst + ((long long)ch * plane + pix) * 8) = pack_x8(v, half);
+    }
   }
 }
 
@@ -604,7 +658,8 @@ __device__ __forceinline__ uint4 x8_max(const uint4& a, const uint4& b, int half
 
 // k x k pooling (stride k): one thread per (chunk, output pixel); source and destination may use different layouts
 __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
-                                int Hin, int Win, int k, int mode, long long ncap_in, long long ncap_out, int half, int im_in, int im_out) {
+                                int Hin, int Win, int k, int mode, long long ncap_in, long long ncap_out, int half, int im_in, int im_out,
+                                int parts) {
   const int Hout = Hin / k, Wout = Win / k;
   const long long n_out = (long long)n_img * Hout * Wout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
@@ -624,6 +679,29 @@ __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bflo
       img = t2 / Hout;
     }
     const long long o = chunk_off(im_out, ch, img, Y, X, Hout, Wout, ncap_out);
+    if (parts == 2) {
+      // split tensors: pool the joined values (hi + lo is exact in fp32), then split again
+      const long long lo_in = (long long)chunks * ncap_in * Hin * Win * 8, lo_out = (long long)chunks * ncap_out * Hout * Wout * 8;
+      float acc[8];
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+          const long long a = chunk_off(im_in, ch, img, Y * k + dy, X * k + dx, Hin, Win, ncap_in);
+          float f[8];
+          join_x8(__ldg(reinterpret_cast<const uint4*>(src + a)), __ldg(reinterpret_cast<const uint4*>(src + lo_in + a)), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = (dy == 0 && dx == 0) ? f[j] : (mode == 0 ? fmaxf(acc[j], f[j]) : acc[j] + f[j]);
+        }
+      if (mode != 0) {
+        const float inv = 1.0f / (float)(k * k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv;
+      }
+      uint4 hi, lo;
+      split_x8(acc, hi, lo);
+      *reinterpret_cast<uint4*>(dst + o) = hi;
+      *reinterpret_cast<uint4*>(dst + lo_out + o) = lo;
+      continue;
+    }
     if (mode == 0) {
       uint4 acc = __ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y * k, X * k, Hin, Win, ncap_in)));
       for (int dy = 0; dy < k; ++dy)
@@ -673,24 +751,34 @@ __global__ void upsample_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_
 }
 
 __global__ void eltwise_cp8_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                   __nv_bfloat16* __restrict__ dst, long long n_vec, int act, float alpha, int half) {
+                                   __nv_bfloat16* __restrict__ dst, long long n_vec, int act, float alpha, int half, long long lo_vec) {
+  // lo_vec != 0: split tensors, the lo part lies lo_vec 16-byte vectors behind the hi part
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
-    unpack_x8(__ldg(reinterpret_cast<const uint4*>(a) + i), x, half);
+    if (lo_vec) join_x8(__ldg(reinterpret_cast<const uint4*>(a) + i), __ldg(reinterpret_cast<const uint4*>(a) + lo_vec + i), x);
+    else unpack_x8(__ldg(reinterpret_cast<const uint4*>(a) + i), x, half);
     if (b) {
-      unpack_x8(__ldg(reinterpret_cast<const uint4*>(b) + i), y, half);
+      if (lo_vec) join_x8(__ldg(reinterpret_cast<const uint4*>(b) + i), __ldg(reinterpret_cast<const uint4*>(b) + lo_vec + i), y);
+      else unpack_x8(__ldg(reinterpret_cast<const uint4*>(b) + i), y, half);
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] += y[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], act, alpha);
-    reinterpret_cast<uint4*>(dst)[i] = pack_x8(x, half);
+    if (lo_vec) {
+      uint4 hi, lo;
+      split_x8(x, hi, lo);
+      reinterpret_cast<uint4*>(dst)[i] = hi;
+      reinterpret_cast<uint4*>(dst)[lo_vec + i] = lo;
+    } else {
+      reinterpret_cast<uint4*>(dst)[i] = pack_x8(x, half);
+    }
   }
 }
 
 // CP8 / IM8 16-bit -> NHWC fp32 (debug / parity reads of intermediate tensors)
 __global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n_img, int H, int W,
-                                   long long ncap, int C, int half, int im) {
+                                   long long ncap, int C, int half, int im, long long lo_off) {
   const long long total = n_img * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -700,7 +788,9 @@ __global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float*
     const int y = (int)(pix % H);
     const long long img = pix / H;
     const __nv_bfloat16* e = src + chunk_off(im, c >> 3, img, y, x, H, W, ncap) + (c & 7);
-    dst[i] = half ? __half2float(*reinterpret_cast<const __half*>(e)) : __bfloat162float(*e);
+    float v = half ? __half2float(*reinterpret_cast<const __half*>(e)) : __bfloat162float(*e);
+    if (lo_off) v += __half2float(*reinterpret_cast<const __half*>(e + lo_off));
+    dst[i] = v;
   }
 }
 
@@ -711,7 +801,7 @@ inline int grid_for(long long total, int threads = 256) {
 }
 
 template <int BN>
-size_t conv_smem_bytes(int kc, int stages, int pair) {
+size_t conv_smem_bytes(int kc, int stages, int pair) {  // kc = 8-channel planes per stage, all parts counted
   return (size_t)stages * pair * (kc * 128 * 16) + (size_t)stages * (kc * BN * 16) + (2 * stages + 1) * sizeof(uint64_t) + 16;
 }
 template <int BN>
@@ -762,11 +852,14 @@ CUtensorMap make_cp8_tensor_map(const void* base, int W, int H, int N, int chunk
 // The same CP8 tensor with the 8-channel vector and the x axis described as ONE inner dimension of 64-bit elements (two per
 // pixel): dims (2W, H, N, C/8, 1); box (2 bw, bh, bn, kc, 1); x coordinates are doubled.  The TMA unit works row by row of the
 // innermost dimension, so a box row is bw * 16 bytes instead of 16: a 40-pixel halo box is 24 requests instead of 960.
-CUtensorMap make_cp8_wide_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc) {
+// `parts` == 2: split tensors (hi tensor, then lo tensor `chunks` planes further): the fifth dimension selects the part and
+// one box brings both, [part][kc][pixels][16 B].
+CUtensorMap make_cp8_wide_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc,
+                                     int parts) {
   CUtensorMap m;
-  cuuint64_t dims[5] = {(cuuint64_t)2 * W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)chunks, 1};
+  cuuint64_t dims[5] = {(cuuint64_t)2 * W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)chunks, (cuuint64_t)parts};
   cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)plane * 16, (cuuint64_t)plane * 16 * chunks};
-  cuuint32_t box[5] = {(cuuint32_t)2 * bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)kc, 1};
+  cuuint32_t box[5] = {(cuuint32_t)2 * bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)kc, (cuuint32_t)parts};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (2 * bw > 256) throw Error(FSR_E_INVALID, "wide CP8 box exceeds 256 elements");
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(base), dims, strides, box, estr,
@@ -778,12 +871,12 @@ CUtensorMap make_cp8_wide_tensor_map(const void* base, int W, int H, int N, int 
 
 // 5-D tensor map over an IM8 activation tensor [C/8][H*W][ncap][8], in 64-bit elements: dims (2 ncap, H*W, C/8, 1, 1);
 // box (256, 1, kc, 1, 1) = 128 images at one pixel, kc channel chunks: every chunk is one contiguous 2 KB row.
-CUtensorMap make_im8_tensor_map(const void* base, long long ncap, int HW, int chunks, int kc) {
+CUtensorMap make_im8_tensor_map(const void* base, long long ncap, int HW, int chunks, int kc, int parts) {
   CUtensorMap m;
-  cuuint64_t dims[5] = {(cuuint64_t)2 * ncap, (cuuint64_t)HW, (cuuint64_t)chunks, 1, 1};
+  cuuint64_t dims[5] = {(cuuint64_t)2 * ncap, (cuuint64_t)HW, (cuuint64_t)chunks, (cuuint64_t)parts, 1};
   cuuint64_t strides[4] = {(cuuint64_t)ncap * 16, (cuuint64_t)HW * ncap * 16, (cuuint64_t)HW * ncap * 16 * chunks,
-                           (cuuint64_t)HW * ncap * 16 * chunks};
-  cuuint32_t box[5] = {256, 1, (cuuint32_t)kc, 1, 1};
+                           (cuuint64_t)HW * ncap * 16 * chunks * parts};
+  cuuint32_t box[5] = {256, 1, (cuuint32_t)kc, (cuuint32_t)parts, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -819,9 +912,12 @@ int conv_tc_bn(int cout) { return cout >= 128 ? 128 : (cout >= 64 ? 64 : 32); }
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
-                    cudaStream_t s) {
+                    int parts, float out_scale, int cpad_out, cudaStream_t s) {
   ConvTcParams p{};
   p.half = half;
+  p.parts = parts;
+  p.out_scale = parts == 2 ? out_scale : 1.0f;
+  p.lo_off = parts == 2 ? (long long)(cpad_out / 8) * plane_out * 8 : 0;
   p.H = H; p.W = W; p.N = n_img;
   p.im = im;
   p.ncap = (int)(plane_out / ((long long)H * W));
@@ -847,11 +943,11 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   p.res = res;
   p.out = dst;
   const int tiles_n = ceil_div(n_img, p.bn);
-  CUtensorMap m0 = im ? make_im8_tensor_map(src0, plane0 / ((long long)H * W), H * W, C0 / 8, kc)
-                      : make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc);
+  CUtensorMap m0 = im ? make_im8_tensor_map(src0, plane0 / ((long long)H * W), H * W, C0 / 8, kc, parts)
+                      : make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc, parts);
   CUtensorMap m1 = !src1 ? m0
-                   : im  ? make_im8_tensor_map(src1, plane1 / ((long long)H * W), H * W, C1 / 8, kc)
-                         : make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc);
+                   : im  ? make_im8_tensor_map(src1, plane1 / ((long long)H * W), H * W, C1 / 8, kc, parts)
+                         : make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc, parts);
   const int BN = conv_tc_bn(cout);
   const int n_iters = ksz * ksz * (p.s0 + p.s1);
   // Two image blocks per CTA (every weight slice fetched from L2 feeds two MMAs) where it measured faster on B200: maps of
@@ -867,9 +963,9 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<128>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc, p.stages, 2), s, m0, m1, p);
-    else launch_pdl(conv_tc_kernel<128, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc, p.stages, 1), s, m0, m1, p);
+    p.stages = conv_stages<128>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair);
+    if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<128, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else if (BN == 64) {
     static bool attr = false;
     if (!attr) {
@@ -877,9 +973,9 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<64>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc, p.stages, 2), s, m0, m1, p);
-    else launch_pdl(conv_tc_kernel<64, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc, p.stages, 1), s, m0, m1, p);
+    p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair);
+    if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<64, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else {
     static bool attr = false;
     if (!attr) {
@@ -887,9 +983,9 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<32>(kc, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc, p.stages, 2), s, m0, m1, p);
-    else launch_pdl(conv_tc_kernel<32, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc, p.stages, 1), s, m0, m1, p);
+    p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair);
+    if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<32, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
 }
@@ -905,26 +1001,29 @@ static void conv_rows_geometry(int H, int W, int& pitch, int& box_rows, int& til
   box_rows = span + 2;
 }
 
-static size_t conv_rows_stage_bytes(int kc, int box_rows, int pitch) {
+static size_t conv_rows_stage_bytes(int kc, int box_rows, int pitch) {  // kc = planes per box, all parts counted
   return ((size_t)kc * box_rows * pitch * 16 + 2 * pitch * 16 + 127) & ~(size_t)127;
 }
 
-bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc) {
+bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc, int parts) {
   if (ksz != 3 || (W != 16 && W != 32) || (cout != 32 && cout != 64)) return false;
   if ((H * (W + 8)) % 128) return false;
   if (kc != 2 && kc != 4) return false;
   int pitch, box_rows, tiles_per_img;
   conv_rows_geometry(H, W, pitch, box_rows, tiles_per_img);
-  const size_t w_bytes = (size_t)9 * ((C0 + C1) / 8) * cout * 16;
-  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + 3 * conv_rows_stage_bytes(kc, box_rows, pitch) + 512;  // >= 3 stages
+  const size_t w_bytes = (size_t)parts * 9 * ((C0 + C1) / 8) * cout * 16;
+  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + 3 * conv_rows_stage_bytes(kc * parts, box_rows, pitch) + 512;  // >= 3 stages
   return smem <= 200 * 1024;
 }
 
 void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                          const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                          long long plane_out, int n_img, int H, int W, int cout, int act, float alpha, int half, int n_sms,
-                         cudaStream_t s) {
+                         int parts, float out_scale, cudaStream_t s) {
   ConvRowsParams p{};
+  p.parts = parts;
+  p.out_scale = parts == 2 ? out_scale : 1.0f;
+  p.lo_off = parts == 2 ? (long long)(cout / 8) * plane_out * 8 : 0;
   p.H = H; p.W = W; p.N = n_img;
   conv_rows_geometry(H, W, p.pitch, p.box_rows, p.tiles_per_img);
   p.pitch_magic = (unsigned)((0x100000000ull + p.pitch - 1) / p.pitch);
@@ -938,11 +1037,11 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   p.cout = cout; p.act = act; p.alpha = alpha; p.half = half;
   p.plane = plane_out;
   p.wpack = wpack;
-  p.w_bytes = 9 * (p.g0 + p.g1) * kc * cout * 16;
+  p.w_bytes = parts * 9 * (p.g0 + p.g1) * kc * cout * 16;
   p.bias = bias; p.res = res; p.out = dst;
-  CUtensorMap m0 = make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.pitch, p.box_rows, 1, kc);
-  CUtensorMap m1 = src1 ? make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.pitch, p.box_rows, 1, kc) : m0;
-  const size_t w_round = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023), stage_bytes = conv_rows_stage_bytes(kc, p.box_rows, p.pitch);
+  CUtensorMap m0 = make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.pitch, p.box_rows, 1, kc, parts);
+  CUtensorMap m1 = src1 ? make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.pitch, p.box_rows, 1, kc, parts) : m0;
+  const size_t w_round = ((size_t)(p.w_bytes + 1023) & ~(size_t)1023), stage_bytes = conv_rows_stage_bytes(kc * parts, p.box_rows, p.pitch);
   p.stages = (int)std::min<size_t>(kRowMaxStages, (200 * 1024 - 512 - w_round) / stage_bytes);
   const size_t smem = w_round + (size_t)p.stages * stage_bytes + 512;  // barriers (256 B) + bias (256 B)
   const int grid = p.n_mtiles < n_sms ? p.n_mtiles : n_sms;
@@ -965,16 +1064,16 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
 }
 
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
-                       int chunks, int half, cudaStream_t s) {
-  pack_small_kernel<<<grid_for(n_pix * chunks), 256, 0, s>>>(s0, c0, s1, c1, dst, n_pix, plane, chunks, half);
+                       int chunks, int half, int parts, cudaStream_t s) {
+  pack_small_kernel<<<grid_for(n_pix * chunks), 256, 0, s>>>(s0, c0, s1, c1, dst, n_pix, plane, chunks, half, parts);
   FSR_LAUNCH_CHECK();
 }
 
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, int half, int im_in, int im_out, cudaStream_t s) {
+                     long long plane_in, long long plane_out, int half, int im_in, int im_out, int parts, cudaStream_t s) {
   const long long ncap_in = plane_in / ((long long)Hin * Win), ncap_out = plane_out / ((long long)(Hin / k) * (Win / k));
   pool_cp8_kernel<<<grid_for((long long)n_img * (Hin / k) * (Win / k) * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, k, mode,
-                                                                                                ncap_in, ncap_out, half, im_in, im_out);
+                                                                                                ncap_in, ncap_out, half, im_in, im_out, parts);
   FSR_LAUNCH_CHECK();
 }
 
@@ -987,14 +1086,14 @@ void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunk
 }
 
 void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
-                        int half, cudaStream_t s) {
-  eltwise_cp8_kernel<<<grid_for(n_vec), 256, 0, s>>>(a, b, dst, n_vec, act, alpha, half);
+                        int half, long long lo_vec, cudaStream_t s) {
+  eltwise_cp8_kernel<<<grid_for(n_vec), 256, 0, s>>>(a, b, dst, n_vec, act, alpha, half, lo_vec);
   FSR_LAUNCH_CHECK();
 }
 
 void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, long long plane, int C, int half, int im,
-                        cudaStream_t s) {
-  cp8_to_nhwc_kernel<<<grid_for(n_img * H * W * C), 256, 0, s>>>(src, dst, n_img, H, W, plane / ((long long)H * W), C, half, im);
+                        long long lo_off, cudaStream_t s) {
+  cp8_to_nhwc_kernel<<<grid_for(n_img * H * W * C), 256, 0, s>>>(src, dst, n_img, H, W, plane / ((long long)H * W), C, half, im, lo_off);
   FSR_LAUNCH_CHECK();
 }
 

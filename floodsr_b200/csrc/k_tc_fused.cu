@@ -34,7 +34,8 @@ namespace fsr {
 
 using namespace tc;
 
-CUtensorMap make_cp8_wide_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc);
+CUtensorMap make_cp8_wide_tensor_map(const void* base, int W, int H, int N, int chunks, long long plane, int bw, int bh, int bn, int kc,
+                                     int parts);
 
 namespace {
 
@@ -584,7 +585,7 @@ void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_
   }
   p.b2 = b2 ? b2[0] : 0.0f;
   // L as TMA source: one LR row of 32 cells, all 4 channel planes -> [4 planes][32 cells][8] (the convT B operand)
-  CUtensorMap mL = make_cp8_wide_tensor_map(lr, kCells, H / kUp, n_img, 4, lr_plane, kCells, 1, 1, 4);
+  CUtensorMap mL = make_cp8_wide_tensor_map(lr, kCells, H / kUp, n_img, 4, lr_plane, kCells, 1, 1, 4, 1);
   const int grid = p.total_rows < n_sms ? (int)p.total_rows : n_sms;
   auto go = [&](auto kernel) {
     FSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

@@ -199,5 +199,27 @@ __device__ __forceinline__ void unpack_x8(const uint4& q, float (&f)[8], int hal
   }
 }
 
+
+// ---- split ("fp16 x 3") operands ---------------------------------------------------------------------------
+// The fp32-tolerance mode keeps every activation and weight as a PAIR of fp16 numbers, value = hi + lo with
+// hi = fp16(value), lo = fp16(value - hi) (22 significant bits), stored as two CP8 tensors one behind the other
+// ("parts").  A product a * b is then three tensor-core MMAs, a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, accumulated in
+// fp32 in TMEM (the dropped lo*lo term is 2^-22 of the product).
+__device__ __forceinline__ void split_x8(const float (&v)[8], uint4& hi, uint4& lo) {
+  float r[8];
+  hi = pack_x8(v, 1);
+  unpack_x8(hi, r, 1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = v[i] - r[i];
+  lo = pack_x8(r, 1);
+}
+__device__ __forceinline__ void join_x8(const uint4& hi, const uint4& lo, float (&f)[8]) {
+  float r[8];
+  unpack_x8(hi, f, 1);
+  unpack_x8(lo, r, 1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] += r[i];
+}
+
 }  // namespace tc
 }  // namespace fsr

@@ -43,7 +43,7 @@ class ModelIOContract:
     scale: int
 
 
-_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16, "fp32_simt": _lib.PREC_FP32_SIMT}
 
 
 def _parse_ref_stats(ref_stats: dict[str, float]) -> tuple[float, float, float]:

@@ -38,9 +38,11 @@ extern "C" {
 #define FSR_E_UNSUPPORTED -4
 
 /* precision modes of the network forward pass */
-#define FSR_PREC_FP32 0 /* fp32 CUDA-core FMA path: <=1e-4 m vs the fp32 oracle            */
+#define FSR_PREC_FP32 0 /* fp32-tolerance mode (<=1e-4 m vs the fp32 oracle) on tcgen05 tensor cores: every activation and
+                           weight is a split fp16 pair (hi, lo), three MMAs per product, fp32 accumulate in TMEM      */
 #define FSR_PREC_BF16 1 /* tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM     */
 #define FSR_PREC_FP16 2 /* same kernels with fp16 operands/activations (3 more mantissa bits)  */
+#define FSR_PREC_FP32_SIMT 3 /* diagnostic: plain fp32 FMA on the CUDA cores (independent check of the tensor-core modes) */
 
 /* window methods of the tile loop (floodsr/models/ResUNet_16x_DEM.py:297, :315) */
 #define FSR_WINDOW_HARD 0

@@ -23,16 +23,18 @@ def _act(x, op):
 
 def _conv(x_nhwc, w_hwio, bias, k):
     x = x_nhwc.permute(0, 3, 1, 2)
-    w = torch.from_numpy(np.ascontiguousarray(w_hwio)).permute(3, 2, 0, 1)
-    b = torch.from_numpy(bias) if bias is not None else None
+    w = torch.from_numpy(np.ascontiguousarray(w_hwio)).permute(3, 2, 0, 1).to(x.dtype)
+    b = torch.from_numpy(bias).to(x.dtype) if bias is not None else None
     return F.conv2d(x, w, b, padding=k // 2).permute(0, 2, 3, 1)
 
 
-def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray) -> np.ndarray:
-    """depth_norm [B,lr,lr], dem_norm [B,hr,hr] -> pred_norm [B,hr,hr]."""
+def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray, dtype=torch.float32, return_all: bool = False):
+    """depth_norm [B,lr,lr], dem_norm [B,hr,hr] -> pred_norm [B,hr,hr] (or every plan tensor, NHWC, with `return_all`).
+
+    `dtype=torch.float64` gives the error-budget reference: the same fp32 inputs and weights, arithmetic in double."""
     t: dict[int, torch.Tensor] = {
-        0: torch.from_numpy(np.asarray(depth_norm, np.float32))[..., None],
-        1: torch.from_numpy(np.asarray(dem_norm, np.float32))[..., None],
+        0: torch.from_numpy(np.asarray(depth_norm, np.float32))[..., None].to(dtype),
+        1: torch.from_numpy(np.asarray(dem_norm, np.float32))[..., None].to(dtype),
     }
     with torch.no_grad():
         for op in lm.ops:
@@ -43,7 +45,7 @@ def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray) -
                     y = y + t[op.res]
                 y = _act(y, op)
                 if op.kind == G.OP_HEAD:
-                    y = (y * torch.from_numpy(op.weight2)).sum(dim=3, keepdim=True)
+                    y = (y * torch.from_numpy(op.weight2).to(dtype)).sum(dim=3, keepdim=True)
                     if op.bias2 is not None:
                         y = y + float(op.bias2.reshape(-1)[0])
             elif op.kind == G.OP_POOL:
@@ -53,8 +55,8 @@ def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray) -
                 y = t[op.src0].repeat_interleave(op.k, dim=1).repeat_interleave(op.k, dim=2)
             elif op.kind == G.OP_CONVT:
                 x = t[op.src0].permute(0, 3, 1, 2)
-                w = torch.from_numpy(np.ascontiguousarray(op.weight)).permute(2, 3, 0, 1)  # [kh,kw,ci,co] -> [ci,co,kh,kw]
-                b = torch.from_numpy(op.bias) if op.bias is not None else None
+                w = torch.from_numpy(np.ascontiguousarray(op.weight)).permute(2, 3, 0, 1).to(dtype)  # [kh,kw,ci,co] -> [ci,co,kh,kw]
+                b = torch.from_numpy(op.bias).to(dtype) if op.bias is not None else None
                 y = _act(F.conv_transpose2d(x, w, b, stride=op.k).permute(0, 2, 3, 1), op)
             elif op.kind == G.OP_ELTWISE:
                 y = t[op.src0] if op.src1 < 0 else t[op.src0] + t[op.src1]
@@ -63,4 +65,6 @@ def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray) -
                 raise AssertionError(op.kind)
             assert tuple(y.shape[1:]) == lm.tensors[op.dst], (op.name, y.shape, lm.tensors[op.dst])
             t[op.dst] = y.contiguous()
+    if return_all:
+        return {k: v.numpy() for k, v in t.items()}
     return t[lm.out_tensor][..., 0].numpy()

@@ -2,6 +2,9 @@
 
 Bit-exact: window geometry, DEM statistics and normalisation, mosaic arithmetic.  Tolerance-level: anything
 through log1p/expm1 (libm vs CUDA differ in the last ulp) and the network forward (fp32 <= 1e-4 m).
+
+`precision="fp32"` is the fp32-tolerance mode on tcgen05 (split fp16 operands, three MMAs per product); the plain
+fp32 CUDA-core kernels stay available as `precision="fp32_simt"` and are used here as a second, independent check.
 """
 
 from __future__ import annotations
@@ -170,6 +173,33 @@ def test_forward_stage_fp32_close_to_oracle(engine, oracle_engine):
     assert want.std() > 0.02
 
 
+def test_fp32_mode_runs_on_tensor_cores_and_agrees_with_the_cuda_core_kernels(engine, h1_model_fp, oracle_engine, monkeypatch):
+    """The <= 1e-4 m mode three ways: fused split kernel, split LR layers + fp32 FMA high-resolution pair, all fp32 FMA."""
+    from floodsr_b200.engine import EngineB200
+    from oracle import preprocessing_np as pp
+
+    b = 5  # not a multiple of anything: ragged row ranges per SM
+    dn = np.stack([pp.scale_depth_log1p(synth_depth(32, 32, seed=30 + i), 5.0) for i in range(b)])
+    en = np.stack([pp.normalize_dem(synth_dem(512, 512, seed=30 + i))[0] for i in range(b)])
+    want = oracle_engine.forward_norm(dn[:2], en[:2])
+    got = engine.stage_forward(dn, en)
+    assert np.abs(got[:2] - want).max() <= 1e-5
+    simt = EngineB200(h1_model_fp, precision="fp32_simt")
+    ref = simt.stage_forward(dn, en)
+    simt.close()
+    assert np.abs(ref[:2] - want).max() <= 1e-5
+    assert np.abs(got - ref).max() <= 1e-5
+    monkeypatch.setenv("FSR_X3_HR_SIMT", "1")
+    pair = EngineB200(h1_model_fp, precision="fp32")
+    monkeypatch.delenv("FSR_X3_HR_SIMT")
+    mid = pair.stage_forward(dn, en)
+    # the low-resolution result is identical (same kernels); only the high-resolution layers differ
+    assert np.array_equal(pair.debug_tensor(37, b), engine.debug_tensor(37, b))
+    pair.close()
+    assert np.abs(mid - got).max() <= 5e-6
+    assert np.array_equal(engine.stage_forward(dn, en), got)  # deterministic
+
+
 # ---------------------------------------------------------------------------------------------------------
 # a1-a4: the engine contract (mirror of the reference's tests/test_engine_contracts.py:63-93)
 # ---------------------------------------------------------------------------------------------------------
@@ -280,6 +310,69 @@ def test_run_raster_properties_at_mersch_size(engine):
     assert np.array_equal(hard, pasted)
     # interior of non-overlapped regions of the feather mosaic equals the hard tile there
     assert np.array_equal(out1[:384, :384], hard[:384, :384])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs 2-4 against the oracle's tile loop (oracle/stitch_np.run_tiled over the torch-CPU network)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _wet_mask_agrees(got, want, tol):
+    flips = (got > 0.01) != (want > 0.01)
+    err = np.abs(got - want)
+    return (not flips.any()) or float(np.abs(want[flips] - 0.01).max()) <= float(err[flips].max()) <= tol
+
+
+@pytest.mark.parametrize("method", ["feather", "hard"])
+def test_config2_mersch_size_raster_vs_oracle(engine, oracle_engine, method):
+    """BASELINE config 2: 4096 x 4096 model-space raster, 121 feather / 64 hard windows; fp32 mode <= 1e-4 m."""
+    from oracle.stitch_np import run_tiled
+
+    h = w = 4096
+    depth, dem = synth_raster(h, w, seed=77)
+    want, n_tiles, summary = run_tiled(oracle_engine, depth, dem, window_method=method, overlap_lr=8)
+    got, got_n, got_summary = engine.run_raster(depth, dem, window_method=method)
+    assert got_n == n_tiles == (121 if method == "feather" else 64) and got_summary == summary
+    assert np.abs(got - want).max() <= FP32_TOL_M
+    assert _wet_mask_agrees(got, want, FP32_TOL_M)
+
+
+def test_config3_batch_of_256_distinct_tiles_vs_oracle(engine, oracle_engine, h1_model_fp):
+    """BASELINE config 3: 256 independent tiles; fp32 mode <= 1e-4 m and fp16 mode <= 1e-2 m + wet/dry mask, every tile
+    against the oracle's run_tile."""
+    from floodsr_b200.engine import EngineB200
+
+    n = 256
+    depth = np.stack([synth_depth(32, 32, seed=500 + i) for i in range(n)])
+    dem = np.stack([synth_dem(512, 512, seed=500 + i) for i in range(n)])
+    want = [oracle_engine.run_tile(depth[i], dem[i]) for i in range(n)]
+    got32 = engine.run_tiles(depth, dem, want_norm=False)
+    fp16 = EngineB200(h1_model_fp, precision="fp16")
+    got16 = fp16.run_tiles(depth, dem, want_norm=False)
+    fp16.close()
+    for i in range(n):
+        assert got32["dem_stats_used"][i] == want[i]["dem_stats_used"] == got16["dem_stats_used"][i], i
+        assert np.abs(got32["prediction_m"][i] - want[i]["prediction_m"]).max() <= FP32_TOL_M, i
+        assert np.abs(got16["prediction_m"][i] - want[i]["prediction_m"]).max() <= 1e-2, i
+        assert _wet_mask_agrees(got16["prediction_m"][i], want[i]["prediction_m"], 1e-2), i
+
+
+def test_config4_8k_raster_vs_oracle(engine, oracle_engine, h1_model_fp):
+    """BASELINE config 4: 8192 x 8192 raster (512 x 512 lores), 441 feather windows; fp32 mode <= 1e-4 m, fp16 <= 1e-2 m."""
+    from floodsr_b200.engine import EngineB200
+    from oracle.stitch_np import run_tiled
+
+    h = w = 8192
+    depth, dem = synth_raster(h, w, seed=88)
+    want, n_tiles, summary = run_tiled(oracle_engine, depth, dem, window_method="feather", overlap_lr=8)
+    got, got_n, got_summary = engine.run_raster(depth, dem)
+    assert got_n == n_tiles == 441 and got_summary == summary
+    assert np.abs(got - want).max() <= FP32_TOL_M
+    fp16 = EngineB200(h1_model_fp, precision="fp16")
+    got16, _, _ = fp16.run_raster(depth, dem)
+    fp16.close()
+    assert np.abs(got16 - want).max() <= 1e-2
+    assert _wet_mask_agrees(got16, want, 1e-2)
 
 
 def test_run_raster_input_assertions(engine):
