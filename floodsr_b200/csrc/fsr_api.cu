@@ -55,6 +55,9 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
                 "op references a tensor outside the plan");
     auto off_ok = [&](int off) { return off == -1 || (off >= 0 && (size_t)off < weights_count); };
     FSR_REQUIRE(off_ok(op.w_off) && off_ok(op.b_off) && off_ok(op.w2_off) && off_ok(op.b2_off), "weight offset outside blob");
+    for (int sidx : {op.src0, op.src1, op.res})  // every operand is a graph input or was written by an earlier op
+      FSR_REQUIRE(sidx < 0 || sidx <= 1 || producer[sidx] >= 0, "plan op reads a tensor that no earlier op has produced");
+    FSR_REQUIRE(op.dst > 1 && producer[op.dst] < 0, "plan op overwrites a graph input or an already produced tensor");
     bool hr = big_[op.dst] || big_[op.src0] || (op.src1 >= 0 && big_[op.src1]) || (op.res >= 0 && big_[op.res]);
     if (op.kind == FSR_OP_HEAD) hr = true;
     op_hr_[i] = hr ? 1 : 0;
@@ -467,6 +470,8 @@ static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, f
   if (row_end < 0) row_end = b.n_rows;
   if (row_end <= row_begin) return;
   const bool first = row_begin == 0;  // only the band's first rows start from the previous band's partial sums
+  FSR_REQUIRE(!d_halo_in || halo_rows_in <= b.n_rows,
+              "band owns fewer rows than the incoming halo covers: merge window rows when planning bands (dist.chain_safe_bands)");
   ProfScope scope(e.prof, PROF_BLEND, s);
   launch_blend(tiles.as<float>(), b.ty0, b.ty1, g, b.row0 + row_begin, row_end - row_begin, first ? d_halo_in : nullptr,
                first ? halo_rows_in : 0, true, b.max_depth, d_out_rows + (size_t)row_begin * g.W, s);
@@ -630,6 +635,13 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   if (ny >= 3 && rows_per_band > 1) band_ty.push_back(1);
   while (band_ty.back() + rows_per_band < ny) band_ty.push_back(band_ty.back() + rows_per_band);
   band_ty.push_back(ny);
+  // a band must own at least the rows it receives partial sums for (three or more window rows covering one coordinate:
+  // overlap >= tile / 2 or a forced trailing window): such a band takes over the following window rows
+  for (size_t b = 1; b + 1 < band_ty.size();) {
+    const int halo_end = std::min(e.win.ys[band_ty[b] - 1] + T, (int)H);
+    if (band_ty[b + 1] < ny && std::min(e.win.ys[band_ty[b + 1]], (int)H) < halo_end) band_ty.erase(band_ty.begin() + b + 1);
+    else ++b;
+  }
   const int n_bands = (int)band_ty.size() - 1;
   e.d_halo[0].ensure((size_t)T * W * sizeof(float));
   e.d_halo[1].ensure((size_t)T * W * sizeof(float));

@@ -45,7 +45,7 @@ def plan_bands(h: int, w: int, hr_tile: int, window_method: str, overlap_hr: int
     ny = len(ys)
     plans: list[BandPlan] = []
     prev_halo = 0
-    for rank, (ty0, ty1) in enumerate(split_tile_rows(ny, world)):
+    for rank, (ty0, ty1) in enumerate(chain_safe_bands(split_tile_rows(ny, world), ys, hr_tile, h)):
         if ty1 <= ty0:
             plans.append(BandPlan(rank, ty0, ty1, h, 0, 0, 0, h, 0))
             continue
@@ -57,6 +57,37 @@ def plan_bands(h: int, w: int, hr_tile: int, window_method: str, overlap_hr: int
         plans.append(BandPlan(rank, ty0, ty1, row0, max(row_end - row0, 0), halo_out, prev_halo, in_row0, max(in_end - in_row0, 0)))
         prev_halo = halo_out
     return plans, ys, xs
+
+
+def chain_safe_bands(bands: list[tuple[int, int]], ys: list[int], hr_tile: int, h: int) -> list[tuple[int, int]]:
+    """Move band boundaries so that every band OWNS at least the rows it receives partial sums for.
+
+    A band's incoming halo ends where the previous band's last window ends.  When window rows overlap so much that a
+    coordinate is covered by three or more of them (overlap >= tile / 2, or a forced trailing window close to its
+    predecessor: `build_tile_starts`, floodsr/tiling.py:7-16), that point can lie beyond the next band's first window
+    row; the rows past the band's own would have nowhere to go.  Such a band takes over the following window rows until
+    its owned rows reach the end of the incoming halo; bands emptied that way move to the end of the list.
+    """
+    ny = len(ys)
+    out: list[tuple[int, int]] = []
+    ty0 = 0
+    for _, want_end in bands:
+        if ty0 >= ny:
+            break
+        ty1 = max(want_end, ty0 + 1) if want_end > ty0 else ty0
+        if ty1 <= ty0:
+            continue
+        if ty0 > 0:
+            halo_end = min(ys[ty0 - 1] + hr_tile, h)
+            while ty1 < ny and min(ys[ty1], h) < halo_end:
+                ty1 += 1
+        out.append((ty0, ty1))
+        ty0 = ty1
+    if out and out[-1][1] < ny:
+        out[-1] = (out[-1][0], ny)
+    while len(out) < len(bands):
+        out.append((ny, ny))
+    return out
 
 
 def exchange_halo(plan: BandPlan, plans: list[BandPlan], halo_out, make_recv, dist_mod, group=None):

@@ -350,10 +350,14 @@ class _Lowering:
         ta, tb = self.single(node, va), self.single(node, vb)
         if self.tensors[ta] != self.tensors[tb] or va.layout != vb.layout:
             self.fail(node, "Add operands must have identical shapes (no broadcasting)")
-        # residual add folded into the convolution that produced one operand
+        # residual add folded into the convolution that produced one operand -- only when the other operand already exists
+        # at that point of the plan (a shortcut convolution emitted AFTER the main branch must not be read before it ran)
+        def born(tid: int) -> int:
+            return next((i for i, op in enumerate(self.ops) if op.dst == tid), -1)  # graph inputs: -1
+
         for mine, other, v in ((a_name, tb, va), (b_name, ta, vb)):
             prod = self.fusable_producer(mine, kinds=(OP_CONV,))
-            if prod is not None and prod.act == ACT_NONE and prod.res < 0:
+            if prod is not None and prod.act == ACT_NONE and prod.res < 0 and born(other) < v.producer:
                 prod.res = other
                 self.vals[node.outputs[0]] = _Val(v.tids, v.layout, v.producer)
                 return

@@ -38,7 +38,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, h, w, out_dir):
+def _worker(rank, world, port, h, w, out_dir, overlap_lr=8):
     sys.path.insert(0, str(REPO))
     from floodsr_b200.dist import plan_bands, run_band_step
     from floodsr_b200.synth import synth_raster
@@ -49,9 +49,9 @@ def _worker(rank, world, port, h, w, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         depth, dem = synth_raster(h, w, seed=h + w)
-        plans, ys, xs = plan_bands(h, w, 512, "feather", 128, world)
+        plans, ys, xs = plan_bands(h, w, 512, "feather", overlap_lr * 16, world)
         plan = plans[rank]
-        ex = NumpyBandExecutor(AnalyticEngine(), h, w)
+        ex = NumpyBandExecutor(AnalyticEngine(), h, w, overlap_hr=overlap_lr * 16)
         rows = None
         if not plan.empty:
             r0 = plan.in_row0
@@ -62,17 +62,20 @@ def _worker(rank, world, port, h, w, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("h,w,world", [(1552, 1040, 2), (2048, 1024, 3), (512, 1024, 2)])
-def test_band_exchange_over_gloo_is_bit_identical_to_single_process(tmp_path, h, w, world):
+@pytest.mark.parametrize("h,w,world,overlap_lr", [(1552, 1040, 2, 8), (2048, 1024, 3, 8), (512, 1024, 2, 8),
+                                                  (1536, 1024, 3, 12), (2048, 528, 3, 20)])
+def test_band_exchange_over_gloo_is_bit_identical_to_single_process(tmp_path, h, w, world, overlap_lr):
+    """overlap_lr 12 at H = 1536 gives window rows [0, 320, 640, 960, 1024] (forced trailing window) and overlap_lr 20 covers
+    coordinates with three window rows: bands must then own at least the rows of their incoming halo (dist.chain_safe_bands)."""
     from floodsr_b200.dist import plan_bands
     from floodsr_b200.synth import synth_raster
     from oracle.stitch_np import run_tiled
 
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, h, w, str(tmp_path)), nprocs=world, join=True)
-    plans, _, _ = plan_bands(h, w, 512, "feather", 128, world)
+    mp.spawn(_worker, args=(world, port, h, w, str(tmp_path), overlap_lr), nprocs=world, join=True)
+    plans, _, _ = plan_bands(h, w, 512, "feather", overlap_lr * 16, world)
     got = np.concatenate([np.load(tmp_path / f"rows_{r}.npy") for r in range(world)], axis=0)
     depth, dem = synth_raster(h, w, seed=h + w)
-    want, n_tiles, _ = run_tiled(AnalyticEngine(), depth, dem, window_method="feather", overlap_lr=8)
+    want, n_tiles, _ = run_tiled(AnalyticEngine(), depth, dem, window_method="feather", overlap_lr=overlap_lr)
     assert sum(p.n_rows for p in plans) == h
     assert got.shape == want.shape and np.array_equal(got, want)

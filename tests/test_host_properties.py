@@ -22,10 +22,11 @@ def test_tile_starts_cover_the_axis(n_tiles, tile, overlap):
 
 
 @settings(max_examples=150, deadline=None)
-@given(h=st.integers(16, 9000), w=st.integers(16, 3000), world=st.integers(1, 9), method=st.sampled_from(["feather", "hard"]))
-def test_band_plans_partition_rows_and_chain_halos(h, w, world, method):
+@given(h=st.integers(16, 9000), w=st.integers(16, 3000), world=st.integers(1, 9), method=st.sampled_from(["feather", "hard"]),
+       overlap=st.sampled_from([128, 128, 64, 192, 320, 400]))
+def test_band_plans_partition_rows_and_chain_halos(h, w, world, method, overlap):
     h, w = h // 16 * 16, w // 16 * 16
-    plans, ys, xs = plan_bands(h, w, 512, method, 128, world)
+    plans, ys, xs = plan_bands(h, w, 512, method, overlap, world)
     assert len(plans) == world
     live = [p for p in plans if not p.empty]
     assert live and live[0].ty0 == 0 and live[-1].ty1 == len(ys)
@@ -37,12 +38,16 @@ def test_band_plans_partition_rows_and_chain_halos(h, w, world, method):
     assert live[0].halo_in_rows == 0 and live[-1].halo_out_rows == 0
     assert all(a.halo_out_rows == b.halo_in_rows for a, b in zip(live, live[1:]))
     assert all(0 <= p.halo_out_rows <= 512 for p in live)
+    # a band owns at least the rows it receives partial sums for, whatever the overlap (three or more window rows may
+    # cover one coordinate): nothing of an incoming halo is left without an owner
+    assert all(p.n_rows >= p.halo_in_rows for p in live)
+    assert all(not p.empty for p in plans[: len(live)]) and all(p.empty for p in plans[len(live):])
     # every band's input rows contain the rows its windows read (clipped to the raster)
     for p in live:
         assert p.in_row0 == min(ys[p.ty0], h) and p.in_row0 + p.in_rows == min(ys[p.ty1 - 1] + 512, h)
     if method == "hard":
         assert all(p.halo_out_rows == 0 for p in live)
-    assert ys == window_grid(h, w, 512, method, 128)[0]
+    assert ys == window_grid(h, w, 512, method, overlap)[0]
 
 
 @settings(max_examples=200, deadline=None)

@@ -86,10 +86,40 @@ def test_lowered_plan_matches_oracle_interpreter(h1_model_fp):
     assert want.std() > 0.02  # the random-init net produces a non-trivial field
 
 
-def _tiny_model(extra_nodes, rewire=None):
-    """H1 with a few nodes replaced, to exercise lowering branches."""
-    m = build_h1_model(seed=1)
-    return m
+def _check_against_oracle(fp, seed=5, tol=5e-6):
+    lm = G.lower_onnx(fp)
+    depth, dem = synth_tile(seed)
+    dn = pp.scale_depth_log1p(depth, 5.0)[None]
+    en = pp.normalize_dem(dem)[0][None]
+    want = OracleEngine(fp).forward_norm(dn, en)
+    assert np.abs(run_plan(lm, dn, en) - want).max() < tol
+    return lm
+
+
+def test_shortcut_conv_emitted_after_the_main_branch_is_not_read_before_it_ran(tmp_path):
+    """conv1, conv2, conv_sc, Add(conv2, conv_sc): the residual must be folded into conv_sc (reading conv2), never into
+    conv2 (which would read conv_sc before it exists)."""
+    m = build_h1_model(seed=4)
+    add_i = next(i for i, n in enumerate(m.nodes) if n.op_type == "Add")
+    add = m.nodes[add_i]
+    y_name, b_name = add.inputs  # y = block input after the projection, b = second body conv
+    c = m.initializers[next(n for n in m.nodes if n.outputs == [b_name]).inputs[1]].shape[0]
+    rng = np.random.default_rng(1)
+    m.initializers["sc_W"] = (rng.standard_normal((c, c, 1, 1)) * 0.1).astype(np.float32)
+    m.initializers["sc_B"] = (rng.standard_normal(c) * 0.05).astype(np.float32)
+    sc = OnnxNode("Conv", [y_name, "sc_W", "sc_B"], ["sc_out"], name="shortcut",
+                  attrs={"dilations": [1, 1], "group": 1, "kernel_shape": [1, 1], "pads": [0, 0, 0, 0], "strides": [1, 1]})
+    m.nodes.insert(add_i, sc)  # after the main branch, right before the Add
+    add.inputs[:] = [b_name, "sc_out"]
+    fp = tmp_path / "shortcut.onnx"
+    save_onnx(m, fp)
+    lm = _check_against_oracle(fp)
+    born = {op.dst: i for i, op in enumerate(lm.ops)}
+    for i, op in enumerate(lm.ops):
+        for src in (op.src0, op.src1, op.res):
+            assert src < 2 or born[src] < i, (i, op.name, src)
+    sc_op = next(op for op in lm.ops if op.name == "shortcut")
+    assert sc_op.res >= 0 and sc_op.k == 1
 
 
 def test_batchnorm_and_bias_add_fold_into_conv(tmp_path):
