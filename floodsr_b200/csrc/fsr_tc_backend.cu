@@ -16,7 +16,7 @@
 namespace fsr {
 
 // launchers implemented in k_tc_conv.cu / k_tc_head.cu
-int conv_tc_bn(int cout);
+int conv_tc_bn(int cout, int parts);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
@@ -178,7 +178,7 @@ void Engine::tc_prepare(const float* w) {
       t.kc = kc;
       t.C0 = C0;
       t.C1 = C1;
-      const int BN = t.rows ? op.cout : conv_tc_bn(op.cout);
+      const int BN = t.rows ? op.cout : conv_tc_bn(op.cout, parts_);
       const int n_tiles = ceil_div(op.cout, BN);
       const int taps = op.k * op.k;
       const int s0 = (C0 / 8) / kc, s1 = C1 ? (C1 / 8) / kc : 0;

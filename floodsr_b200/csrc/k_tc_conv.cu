@@ -82,6 +82,9 @@ struct ConvTcParams {
                            // one output pixel, each tap is ONE contiguous 2 KB run per channel chunk, out-of-range taps are skipped
   int ncap;                // images per pixel plane of IM8 tensors (allocation capacity)
   int parts;               // 1: plain 16-bit operands; 2: split fp16 (hi, lo) operands, three MMAs per product (tc_common.cuh)
+  int nacc;                // parts == 2: the K steps of the hi*hi products rotate over `nacc` TMEM accumulators and the small
+                           // hi*lo / lo*hi products go to one more, all summed in fp32 registers by the epilogue: the tensor core
+                           // truncates when it adds into an accumulator, so error grows with the length of an accumulation chain
   float out_scale;         // parts == 2: the packed weights carry a power-of-two factor, undone here
   long long lo_off;        // parts == 2: elements between the hi and the lo tensor of out / res
   long long plane;         // pixels per CP8 plane of the output/residual tensors (N_capacity * H * W)
@@ -148,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, (uint32_t)(PAIR * BN));
+    tmem_alloc(tmem_slot, (uint32_t)(PAIR * BN * (p.parts == 2 ? p.nacc + 1 : 1)));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -191,7 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a + h * kABytesMax), 128 * 16);
       const uint32_t b_lo0 = desc_lo32(smem_u32(smem_b), BN * 16);
       const uint32_t a_step = (uint32_t)a_stage >> 4, b_step = (uint32_t)kBBytesMax >> 4;
-      const uint32_t d = tmem_base + h * BN;
+      const uint32_t d = tmem_base + h * BN;  // split mode runs with PAIR == 1: accumulators [d, d + (nacc + 1) * BN)
       const int kpairs = p.kc / 2;
       const uint32_t a_part = (uint32_t)(p.kc * 128 * 16) >> 4, b_part = (uint32_t)(p.kc * BN * 16) >> 4;
       const bool leader = elect_one();
@@ -202,13 +205,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         if (leader) {
           // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
-          for (int j = 0; j < kpairs; ++j) {
-            const uint32_t aj = a_lo + j * ((2 * 128 * 16) >> 4), bj = b_lo + j * ((2 * BN * 16) >> 4);
-            umma_lo(d, aj, bj, kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
-            if (p.parts == 2) {  // + a_lo * b_hi + a_hi * b_lo
-              umma_lo(d, aj + a_part, bj, kDescHi, idesc, 1u);
-              umma_lo(d, aj, bj + b_part, kDescHi, idesc, 1u);
+          if (p.parts == 2) {
+            // stage `it` adds its hi*hi products to accumulator it % nacc; + a_lo * b_hi + a_hi * b_lo go to accumulator nacc
+            const uint32_t dm = d + (uint32_t)(it % p.nacc) * BN, ds = d + (uint32_t)p.nacc * BN;
+            for (int j = 0; j < kpairs; ++j) {
+              const uint32_t aj = a_lo + j * ((2 * 128 * 16) >> 4), bj = b_lo + j * ((2 * BN * 16) >> 4);
+              umma_lo(dm, aj, bj, kDescHi, idesc, (it >= p.nacc || j > 0) ? 1u : 0u);
+              umma_lo(ds, aj + a_part, bj, kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+              umma_lo(ds, aj, bj + b_part, kDescHi, idesc, 1u);
             }
+          } else {
+            for (int j = 0; j < kpairs; ++j)
+              umma_lo(d, a_lo + j * ((2 * 128 * 16) >> 4), b_lo + j * ((2 * BN * 16) >> 4), kDescHi, idesc, (it > 0 || j > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
           if (it == n_iters_cta - 1) umma_commit(accum_full);
@@ -246,11 +254,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN;
+      const int n_extra = p.parts == 2 ? (n_iters_cta < p.nacc ? n_iters_cta : p.nacc) : 0;  // accumulators beyond the first
 #pragma unroll
       for (int c = 0; c < BN / 8; ++c) {
         float v[8];
         tmem_ld8(taddr + c * 8, v);
         tmem_ld_wait();
+        if (p.parts == 2) {
+          // fixed summation order: main accumulators 1 .. used - 1, then the small-product accumulator (index nacc)
+          for (int a = 1; a <= n_extra; ++a) {
+            float u[8];
+            tmem_ld8(taddr + (uint32_t)(a == n_extra ? p.nacc : a) * BN + c * 8, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += u[i];
+          }
+        }
         const int co = n_tile * BN + c * 8;
         if (valid && co < p.cout) {
           const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
@@ -296,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)(PAIR * BN));
+    tmem_dealloc(tmem_base, (uint32_t)(PAIR * BN * (p.parts == 2 ? p.nacc + 1 : 1)));
   }
 }
 
@@ -333,6 +352,9 @@ struct ConvRowsParams {
   int half;
   int stages;          // halo-box ring depth (as many as fit beside the weights)
   int parts;           // 1: plain 16-bit operands; 2: split fp16 (hi, lo) operands, three MMAs per product
+  int sets;            // accumulator buffers / epilogue warp sets in use (<= kRowsEpiSets)
+  int nacc;            // parts == 2: hi*hi products rotate over `nacc` accumulators per buffer, the small products use one more
+                       // (see ConvTcParams::nacc); a buffer is then (nacc + 1) * BN TMEM columns
   float out_scale;     // parts == 2: power-of-two factor carried by the packed weights, undone in the epilogue
   long long lo_off;    // parts == 2: elements between the hi and the lo tensor of out / res
   unsigned long long* stats;  // FSR_ROWS_STATS: per-CTA clock totals of the pipeline roles (diagnostics)
@@ -366,6 +388,8 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = p.g0 + p.g1;
+  const int buf_cols = (p.parts == 2 ? p.nacc + 1 : 1) * BN;  // TMEM columns of one accumulator buffer
+  const uint32_t tmem_cols = p.parts == 2 ? (uint32_t)(p.sets * buf_cols) : (uint32_t)kRowsTmemCols<BN>;  // host: a power of two >= 32
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -385,7 +409,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, kRowsTmemCols<BN>);
+    tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
   if (threadIdx.x < BN) s_bias[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.0f;
@@ -458,11 +482,11 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint32_t ph = 0;
     while (s >= p.stages) { s -= p.stages; ph ^= 1; }
     for (int mt = blockIdx.x + e * gridDim.x; mt < p.n_mtiles; mt += kRowsIssuers * gridDim.x, nt += kRowsIssuers) {
-      const int ab = nt % kRowsEpiSets;
-      const uint32_t d = tmem_base + ab * BN;
+      const int ab = nt % p.sets;
+      const uint32_t d = tmem_base + ab * buf_cols;
       const uint32_t c0 = (uint32_t)(t * 128) - __umulhi((unsigned)(t * 128), p.pitch_magic) * (uint32_t)p.pitch;  // column (in the padded pitch) of the tile's first position
       long long c_a = p.stats ? clock64() : 0;
-      mbar_wait(&acc_empty[ab], ((nt / kRowsEpiSets) & 1) ^ 1);
+      mbar_wait(&acc_empty[ab], ((nt / p.sets) & 1) ^ 1);
       if (p.stats) { w_acc += clock64() - c_a; ++n_t; }
       for (int g = 0; g < groups; ++g) {
         c_a = p.stats ? clock64() : 0;
@@ -476,15 +500,22 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t a_t = a_s + (tap / 3) * row_u + (tap % 3);
             const uint32_t b_t = b_g + tap * wtap_u;
-            umma_lo(d, a_t, b_t, kDescHi, idesc, (g > 0 || tap > 0) ? 1u : 0u);
-            if (kpairs > 1) umma_lo(d, a_t + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
-            if (p.parts == 2) {  // + a_lo * w_hi + a_hi * w_lo
-              umma_lo(d, a_t + a_part, b_t, kDescHi, idesc, 1u);
-              umma_lo(d, a_t, b_t + w_part, kDescHi, idesc, 1u);
+            if (p.parts == 2) {
+              // hi*hi products of step q = g * 9 + tap go to accumulator q % nacc (nacc <= 9: every accumulator is written in
+              // the first group); + a_lo * w_hi + a_hi * w_lo to accumulator nacc
+              const int q = g * 9 + tap;
+              const uint32_t dm = d + (uint32_t)(q % p.nacc) * BN, ds = d + (uint32_t)p.nacc * BN;
+              umma_lo(dm, a_t, b_t, kDescHi, idesc, q >= p.nacc ? 1u : 0u);
+              if (kpairs > 1) umma_lo(dm, a_t + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
+              umma_lo(ds, a_t + a_part, b_t, kDescHi, idesc, q > 0 ? 1u : 0u);
+              umma_lo(ds, a_t, b_t + w_part, kDescHi, idesc, 1u);
               if (kpairs > 1) {
-                umma_lo(d, a_t + a_part + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
-                umma_lo(d, a_t + kpl_u, b_t + w_part + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
+                umma_lo(ds, a_t + a_part + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
+                umma_lo(ds, a_t + kpl_u, b_t + w_part + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
               }
+            } else {
+              umma_lo(d, a_t, b_t, kDescHi, idesc, (g > 0 || tap > 0) ? 1u : 0u);
+              if (kpairs > 1) umma_lo(d, a_t + kpl_u, b_t + ((2 * BN * 16) >> 4), kDescHi, idesc, 1u);
             }
           }
           umma_commit(&empty[s]);
@@ -512,14 +543,14 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int set = (warp - 1 - kRowsIssuers) >> 2;
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    // (image, tile-in-image) advance without divisions
-    const int first = blockIdx.x + set * gridDim.x, step = kRowsEpiSets * gridDim.x;
+    // (image, tile-in-image) advance without divisions; warp sets beyond p.sets have no accumulator buffer and no work
+    const int first = set < p.sets ? blockIdx.x + set * gridDim.x : p.n_mtiles, step = p.sets * gridDim.x;
     int img = first / p.tiles_per_img, t = first % p.tiles_per_img;
     const int step_img = step / p.tiles_per_img, step_t = step % p.tiles_per_img;
     int nt = set;
     long long e_wait = 0, e_ld = 0;
     const long long e_start = p.stats ? clock64() : 0;
-    for (int mt = first; mt < p.n_mtiles; mt += step, nt += kRowsEpiSets) {
+    for (int mt = first; mt < p.n_mtiles; mt += step, nt += p.sets) {
       const int ab = set;
       const int pos = t * 128 + m;
       const int y = (int)__umulhi((unsigned)pos, p.pitch_magic), x = pos - y * p.pitch;
@@ -531,15 +562,25 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         for (int c = 0; c < BN / 8; ++c) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)c * p.plane + pix) * 8));
       }
       const long long c_a = p.stats ? clock64() : 0;
-      mbar_wait(&acc_full[ab], (nt / kRowsEpiSets) & 1);
+      mbar_wait(&acc_full[ab], (nt / p.sets) & 1);
       if (p.stats) e_wait += clock64() - c_a;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * buf_cols;
 #pragma unroll
       for (int c32 = 0; c32 < BN / 32; ++c32) {
         float v[32];
         tmem_ld32(taddr + c32 * 32, v);
         tmem_ld_wait();
+        if (p.parts == 2) {
+          // sum of the partial accumulators in a fixed order: main 1 .. nacc - 1, then the small-product accumulator
+          for (int a = 1; a <= p.nacc; ++a) {
+            float u[32];
+            tmem_ld32(taddr + (uint32_t)a * BN + c32 * 32, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += u[i];
+          }
+        }
         if (c32 == BN / 32 - 1) {
           // the accumulator is in registers: hand the buffer back before the arithmetic and the stores
           tc_fence_before();
@@ -599,7 +640,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kRowsTmemCols<BN>);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -805,10 +846,10 @@ size_t conv_smem_bytes(int kc, int stages, int pair) {  // kc = 8-channel planes
   return (size_t)stages * pair * (kc * 128 * 16) + (size_t)stages * (kc * BN * 16) + (2 * stages + 1) * sizeof(uint64_t) + 16;
 }
 template <int BN>
-int conv_stages(int kc, int n_iters, long long n_ctas, int pair) {
+int conv_stages(int kc, int n_iters, long long n_ctas, int pair, bool one_cta_per_sm = false) {
   // few CTAs (deep, narrow levels): one CTA per SM with a deep ring, each K step is L2-latency bound;
   // many CTAs: keep two or more CTAs per SM so that their prologues and epilogues overlap
-  const size_t budget = n_ctas <= (pair > 1 ? 148 : 2 * 148) ? 200 * 1024 : 100 * 1024;
+  const size_t budget = (one_cta_per_sm || n_ctas <= (pair > 1 ? 148 : 2 * 148)) ? 200 * 1024 : 100 * 1024;
   int st = (int)(budget / ((size_t)pair * kc * 128 * 16 + (size_t)kc * BN * 16));
   st = st > kMaxStages ? kMaxStages : st;
   st = st > n_iters ? n_iters : st;
@@ -907,7 +948,8 @@ void conv_tc_tile_box(int H, int W, int& bw, int& bh, int& bn) {
   if (bw * bh * bn != 128 || W % bw || H % bh) throw Error(FSR_E_UNSUPPORTED, "feature-map size does not tile into 128-pixel boxes");
 }
 
-int conv_tc_bn(int cout) { return cout >= 128 ? 128 : (cout >= 64 ? 64 : 32); }
+// output channels per CTA; split mode keeps tiles at <= 64 channels so that up to 8 partial accumulators fit in TMEM
+int conv_tc_bn(int cout, int parts) { return (cout >= 128 && parts == 1) ? 128 : (cout >= 64 ? 64 : 32); }
 
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
@@ -948,13 +990,17 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   CUtensorMap m1 = !src1 ? m0
                    : im  ? make_im8_tensor_map(src1, plane1 / ((long long)H * W), H * W, C1 / 8, kc, parts)
                          : make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc, parts);
-  const int BN = conv_tc_bn(cout);
+  const int BN = conv_tc_bn(cout, parts);
   const int n_iters = ksz * ksz * (p.s0 + p.s1);
+  // split mode: 1, 3 or 7 accumulators for the hi*hi products (+ 1 for the small ones; a power-of-two TMEM allocation), so
+  // that one accumulation chain stays short: the tensor core truncates on every addition into an accumulator
+  const int hh_steps = n_iters * (kc / 2);
+  p.nacc = parts == 2 ? (hh_steps > 48 ? 7 : hh_steps > 12 ? 3 : 1) : 1;
   // Two image blocks per CTA (every weight slice fetched from L2 feeds two MMAs) where it measured faster on B200: maps of
   // <= 16 pixels with enough CTAs left to fill the SMs.  Larger maps have short K loops and many CTAs; there two
   // co-resident single-tile CTAs (8 epilogue warps per SM instead of 4) win.  env FSR_NO_CONV_PAIR disables it.
-  const long long n_single = (long long)p.tiles_x * p.tiles_y * tiles_n * ceil_div(cout, conv_tc_bn(cout));
-  p.pair = (tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR")) ? kConvPairs : 1;
+  const long long n_single = (long long)p.tiles_x * p.tiles_y * tiles_n * ceil_div(cout, BN);
+  p.pair = (parts == 1 && tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR")) ? kConvPairs : 1;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * ceil_div(tiles_n, p.pair)), (unsigned)ceil_div(cout, BN));
   if (BN == 128) {
     static bool attr = false;
@@ -973,7 +1019,7 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair);
+    p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && 64 * (p.nacc + 1) > 256);
     if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<64, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else {
@@ -983,7 +1029,7 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair);
+    p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && 32 * (p.nacc + 1) > 256);
     if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<32, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
   }
@@ -1022,6 +1068,8 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
                          int parts, float out_scale, cudaStream_t s) {
   ConvRowsParams p{};
   p.parts = parts;
+  p.sets = parts == 2 ? 2 : kRowsEpiSets;  // split mode: 2 buffers x (nacc + 1) accumulators x cout columns = 512
+  p.nacc = parts == 2 ? (cout == 64 ? 3 : 7) : 1;
   p.out_scale = parts == 2 ? out_scale : 1.0f;
   p.lo_off = parts == 2 ? (long long)(cout / 8) * plane_out * 8 : 0;
   p.H = H; p.W = W; p.N = n_img;
