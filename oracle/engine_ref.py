@@ -16,6 +16,37 @@ from oracle import preprocessing_np as pp
 from oracle.onnx_ref import RefSession
 
 
+class _OrtSession:
+    """The reference's own session (`ort.InferenceSession(model, providers=[CPUExecutionProvider])`, ort.py:54,193) behind
+    the three calls `OracleEngine` makes.  Only constructed where onnxruntime is importable (it is not in the offline image)."""
+
+    def __init__(self, path, threads: int | None = None):
+        import onnxruntime as ort
+
+        so = ort.SessionOptions()
+        if threads is not None:
+            so.intra_op_num_threads = int(threads)
+        self.sess = ort.InferenceSession(str(path), sess_options=so, providers=["CPUExecutionProvider"])
+        self.version = ort.__version__
+
+    def input_signature(self):
+        return [(i.name, list(i.shape)) for i in self.sess.get_inputs()]
+
+    def output_signature(self):
+        return [(o.name, list(o.shape)) for o in self.sess.get_outputs()]
+
+    def run(self, feeds, want=None):
+        return self.sess.run(want, {k: np.asarray(v, np.float32) for k, v in feeds.items()})
+
+
+def live_ort_available() -> bool:
+    try:
+        import onnxruntime  # noqa: F401
+    except Exception:
+        return False
+    return True
+
+
 def _hwc(dims, name):
     """ort.py:66-73."""
     assert len(dims) == 4, f"{name} must be rank-4 NHWC; got {dims}"
@@ -29,10 +60,19 @@ def _hwc(dims, name):
 class OracleEngine:
     """CPU oracle with the `EngineORT` surface: `.contract`-like attributes and `run_tile`."""
 
-    def __init__(self, model_fp, dtype: torch.dtype = torch.float32, threads: int | None = None):
+    def __init__(self, model_fp, dtype: torch.dtype = torch.float32, threads: int | None = None, backend: str = "auto"):
+        """`backend`: "torch" = the restated interpreter (oracle.onnx_ref), "ort" = a live onnxruntime session (the reference's
+        own arithmetic), "auto" = ort when importable and fp32 is asked for, else torch.  `self.backend` says which one runs."""
         self._model_fp = Path(model_fp).expanduser().resolve()
         assert self._model_fp.exists(), f"model file does not exist: {self._model_fp}"
-        self.session = RefSession(self._model_fp, dtype=dtype, threads=threads)
+        assert backend in ("auto", "torch", "ort")
+        use_ort = backend == "ort" or (backend == "auto" and dtype == torch.float32 and live_ort_available())
+        if use_ort:
+            self.session = _OrtSession(self._model_fp, threads=threads)
+            self.backend = f"onnxruntime {self.session.version} CPUExecutionProvider"
+        else:
+            self.session = RefSession(self._model_fp, dtype=dtype, threads=threads)
+            self.backend = "torch-CPU restatement of the ONNX graph (onnxruntime not importable)"
         # ort.py:75-102
         ins = dict(self.session.input_signature())
         outs = self.session.output_signature()
