@@ -34,8 +34,8 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_REQUIRE(hdr_.lr_tile > 0 && hdr_.hr_tile == hdr_.lr_tile * hdr_.scale, "inconsistent tile geometry");
   FSR_REQUIRE(hdr_.hr_tile % 64 == 0, "hr tile must be a multiple of 64");
   FSR_REQUIRE(hdr_.out_tensor >= 2 && hdr_.out_tensor < hdr_.n_tensors, "bad output tensor");
-  FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_BF16 || precision == FSR_PREC_FP16 || precision == FSR_PREC_FP32_SIMT,
-              "unknown precision mode");
+  FSR_REQUIRE(precision != 1, "precision mode 1 (bf16 operands) was retired: it misses the 1e-2 m bound; use FSR_PREC_FP16");
+  FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_FP16 || precision == FSR_PREC_FP32_SIMT, "unknown precision mode");
   if (const char* e = getenv("FSR_BAND_TILES")) band_tiles_ = std::max(1, atoi(e));
 
   const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
@@ -51,6 +51,11 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   for (size_t i = 0; i < ops_.size(); ++i) {
     const fsr_op& op = ops_[i];
     FSR_REQUIRE(op.kind >= FSR_OP_CONV && op.kind <= FSR_OP_HEAD, "unknown op kind in plan");
+    FSR_REQUIRE(op.act >= FSR_ACT_NONE && op.act <= FSR_ACT_SIGMOID && (op.kind == FSR_OP_ELTWISE || op.act <= FSR_ACT_LEAKY),
+                "activation not supported by this op kind");
+    FSR_REQUIRE(op.kind != FSR_OP_POOL || (op.mode >= FSR_POOL_MAX && op.mode <= FSR_POOL_PICK && (op.mode != FSR_POOL_PICK || (op.aux >= 0 && op.aux < op.k))),
+                "bad pooling mode");
+    FSR_REQUIRE(op.kind != FSR_OP_UPSAMPLE || (op.mode >= FSR_UP_NEAREST && op.mode <= FSR_UP_LINEAR_ASYMMETRIC), "bad upsampling mode");
     FSR_REQUIRE(tensor_ok(op.src0, false) && tensor_ok(op.src1, true) && tensor_ok(op.res, true) && tensor_ok(op.dst, false),
                 "op references a tensor outside the plan");
     auto off_ok = [&](int off) { return off == -1 || (off >= 0 && (size_t)off < weights_count); };
@@ -205,16 +210,16 @@ void Engine::run_ops(bool hr_phase, int n, int sub_start, cudaStream_t s) {
         launch_conv_fp32(s0, ts.c, s1, c1, wp(op.w_off), wp(op.b_off), rs, dst, n, td.h, td.w, op.k, op.cout, op.act, op.alpha, s);
         break;
       case FSR_OP_POOL:
-        launch_pool_fp32(s0, dst, n, ts.h, ts.w, ts.c, op.k, op.mode, s);
+        launch_pool_fp32(s0, dst, n, ts.h, ts.w, ts.c, op.k, op.mode, op.aux, s);
         break;
       case FSR_OP_UPSAMPLE:
-        launch_upsample_fp32(s0, dst, n, ts.h, ts.w, ts.c, op.k, s);
+        launch_upsample_fp32(s0, dst, n, ts.h, ts.w, ts.c, op.k, op.mode, s);
         break;
       case FSR_OP_CONVT:
         launch_convt_fp32(s0, wp(op.w_off), wp(op.b_off), dst, n, ts.h, ts.w, ts.c, op.cout, op.k, op.act, op.alpha, s);
         break;
       case FSR_OP_ELTWISE:
-        launch_eltwise_fp32(s0, s1, dst, (size_t)n * td.h * td.w * td.c, op.act, op.alpha, s);
+        launch_eltwise_fp32(s0, s1, dst, (size_t)n * td.h * td.w * td.c, op.act, op.alpha, op.beta, s);
         break;
       case FSR_OP_HEAD: {
         float* mid = d_headmid_.as<float>();

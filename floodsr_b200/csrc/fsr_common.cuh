@@ -145,6 +145,26 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   return v;
 }
 
+// activations of element-wise ops (the convolution epilogues implement NONE / RELU / LEAKY only)
+__device__ __forceinline__ float apply_act2(float v, int act, float alpha, float beta) {
+  if (act == FSR_ACT_CLIP) return fminf(fmaxf(v, alpha), beta);
+  if (act == FSR_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return apply_act(v, act, alpha);
+}
+
+// Source sample of output coordinate `o` of an f-fold bilinear upsampling (ONNX Resize, mode linear): index of the lower
+// neighbour, clamped, and the weight of the upper one.  n_in = source extent.
+__device__ __forceinline__ void up_linear_coord(int o, int f, int n_in, int mode, int& i0, int& i1, float& w1) {
+  float x;
+  if (mode == FSR_UP_LINEAR_ALIGN_CORNERS) x = n_in * f > 1 ? (float)o * (float)(n_in - 1) / (float)(n_in * f - 1) : 0.0f;
+  else if (mode == FSR_UP_LINEAR_ASYMMETRIC) x = (float)o / (float)f;
+  else x = ((float)o + 0.5f) / (float)f - 0.5f;
+  x = fminf(fmaxf(x, 0.0f), (float)(n_in - 1));
+  i0 = (int)floorf(x);
+  i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+  w1 = x - (float)i0;
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));

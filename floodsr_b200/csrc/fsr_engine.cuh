@@ -59,9 +59,9 @@ void launch_conv_fp32(const float* src0, int C0, const float* src1, int C1, cons
                       cudaStream_t s);
 void launch_convt_fp32(const float* src, const float* w, const float* bias, float* dst, int n_img, int Hin, int Win,
                        int cin, int cout, int k, int act, float alpha, cudaStream_t s);
-void launch_pool_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int k, int mode, cudaStream_t s);
-void launch_upsample_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int f, cudaStream_t s);
-void launch_eltwise_fp32(const float* a, const float* b, float* dst, size_t total, int act, float alpha, cudaStream_t s);
+void launch_pool_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int k, int mode, int aux, cudaStream_t s);
+void launch_upsample_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int f, int mode, cudaStream_t s);
+void launch_eltwise_fp32(const float* a, const float* b, float* dst, size_t total, int act, float alpha, float beta, cudaStream_t s);
 void launch_head_1x1_fp32(const float* feat, const float* w2, const float* b2, float* out, size_t n_pix, int cmid,
                           cudaStream_t s);
 void launch_invert_depth(const float* pred_norm, float* pred_m, size_t n, float max_depth, float denom, cudaStream_t s);
@@ -176,6 +176,7 @@ class Engine {
   void tc_prepare_fused(const float* host_weights);
   void tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
   void run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  bool hr_simt_ = false;                // the high-resolution layers run on the fp32 FMA kernels (shapes the tcgen05 kernels do not cover)
   int parts_ = 1;                       // 2: split fp16 (hi, lo) tensors and weights, three MMAs per product (FSR_PREC_FP32)
   int fused_ct_ = -1, fused_hd_ = -1;   // plan ops run by the fused high-resolution kernel, or -1
   DeviceBuf fused_hw_, fused_wt_;

@@ -1,5 +1,5 @@
 // Tensor-core backend of the Engine (every precision mode but the SIMT diagnostic one): tensor formats, weight packing and
-// op dispatch onto the tcgen05 kernels.  FSR_PREC_BF16 / FSR_PREC_FP16 store activations and weights as one 16-bit tensor;
+// op dispatch onto the tcgen05 kernels.  FSR_PREC_FP16 stores activations and weights as one 16-bit tensor;
 // FSR_PREC_FP32 (the <= 1e-4 m mode) stores every one of them as a split fp16 pair (hi, lo) and runs three MMAs per product
 // (tc_common.cuh: "parts" == 2).
 #include <cuda_bf16.h>
@@ -29,11 +29,11 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
                        int chunks, int half, int parts, cudaStream_t s);
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, int half, int im_in, int im_out, int parts, cudaStream_t s);
+                     long long plane_in, long long plane_out, int half, int im_in, int im_out, int parts, int aux, cudaStream_t s);
 void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
-                         long long plane_in, long long plane_out, int im_in, int im_out, cudaStream_t s);
+                         long long plane_in, long long plane_out, int im_in, int im_out, int mode, int half, int parts, cudaStream_t s);
 void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
-                        int half, long long lo_vec, cudaStream_t s);
+                        float beta, int half, long long lo_vec, cudaStream_t s);
 void launch_cp8_to_nhwc(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, long long plane, int C, int half, int im,
                         long long lo_off, cudaStream_t s);
 void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bfloat16* wpack, const float* bias,
@@ -122,7 +122,7 @@ void split_weight(float v, uint16_t& hi, uint16_t& lo) {
 // Decide per-tensor storage and pack every conv-like op's weights into the layouts the kernels stream.
 void Engine::tc_prepare(const float* w) {
   parts_ = precision_ == FSR_PREC_FP32 ? 2 : 1;
-  g_pack_half = precision_ != FSR_PREC_BF16;
+  g_pack_half = true;  // fp16 storage in every tensor-core mode (the kernels keep a bf16 code path; no mode selects it)
   const int nt = (int)tensors_.size();
   tc_fmt_.assign(nt, 0);
   tc_cpad_.assign(nt, 0);
@@ -136,9 +136,29 @@ void Engine::tc_prepare(const float* w) {
   }
   tc_ops_.clear();
   tc_ops_.resize(ops_.size());
+  // The tensor-core kernels of the high-resolution end cover the transposed-convolution -> head pair at 32 channels (the
+  // shape of the model family's published size); any other high-resolution layer set runs as fp32 FMA kernels on the
+  // low-resolution result (run_hr_simt): correct for every graph the lowering accepts, not a throughput path.
+  hr_simt_ = parts_ == 2;
+  if (parts_ == 1) {
+    std::vector<int> hr_ops;
+    for (size_t i = 0; i < ops_.size(); ++i)
+      if (op_hr_[i]) hr_ops.push_back((int)i);
+    bool ok = hr_ops.size() == 2 && ops_[hr_ops[0]].kind == FSR_OP_CONVT && ops_[hr_ops[1]].kind == FSR_OP_HEAD &&
+              ops_[hr_ops[1]].src0 == ops_[hr_ops[0]].dst;
+    if (ok) {
+      const fsr_op& ct = ops_[hr_ops[0]];
+      const fsr_op& hd = ops_[hr_ops[1]];
+      const int cin = tensors_[ct.src0].c;
+      ok = tc_fmt_[ct.src0] && cin % 16 == 0 && cin <= 64 && ct.cout == 32 && ct.k % (256 / ct.cout) == 0 && hd.cout == 32 && hd.k == 3 &&
+           hd.src1 >= 0 && !tc_fmt_[hd.src1] && tensors_[hd.src1].c == 1;
+    }
+    hr_simt_ = !ok;
+  }
   for (size_t oi = 0; oi < ops_.size(); ++oi) {
     const fsr_op& op = ops_[oi];
     TcOp& t = tc_ops_[oi];
+    if (hr_simt_ && op_hr_[oi]) continue;  // runs on the fp32 kernels (or, in split mode, in the fused split kernel)
     auto need_cp8 = [&](int id, const char* what) {
       if (id >= 0 && !tc_fmt_[id]) throw Error(FSR_E_UNSUPPORTED, std::string("bf16 backend: ") + what + " needs a >= 8-channel tensor");
     };
@@ -159,7 +179,7 @@ void Engine::tc_prepare(const float* w) {
       }
       need_cp8(op.dst, "conv output");
       need_cp8(op.res, "conv residual");
-      FSR_REQUIRE(op.cout % 32 == 0, "bf16 backend: conv output channels must be a multiple of 32");
+      FSR_REQUIRE(op.cout % 16 == 0, "tensor-core backend: conv output channels must be a multiple of 16");
       int kc = std::gcd(C0 / 8, C1 ? C1 / 8 : C0 / 8);
       const int kc_max = parts_ == 2 ? 4 : 8;  // split stages carry two parts: same bytes per stage
       while (kc > kc_max || (kc % 2)) {
@@ -217,9 +237,6 @@ void Engine::tc_prepare(const float* w) {
                 }
       t.wpack.ensure(pk.size() * 2);
       FSR_CUDA(cudaMemcpy(t.wpack.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
-    } else if (parts_ == 2 && (op.kind == FSR_OP_CONVT || op.kind == FSR_OP_HEAD)) {
-      // split mode: the high-resolution end runs in the fused split kernel (tc_prepare_fused)
-      if (op.kind == FSR_OP_CONVT) need_cp8(op.src0, "convT source");
     } else if (op.kind == FSR_OP_CONVT) {
       need_cp8(op.src0, "convT source");
       need_cp8(op.dst, "convT output");
@@ -332,7 +349,7 @@ void Engine::tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, 
   const fsr_op& hd = ops_[fused_hd_];
   const TcOp& th = tc_ops_[fused_hd_];
   const auto& tf = tensors_[ct.dst];
-  const int half = precision_ != FSR_PREC_BF16 ? 1 : 0;
+  const int half = 1;
   float* pn = tbase_[hd.dst];  // may be nullptr when the caller does not want the normalised prediction
   float* pm = d_pred_m;
   if (!pm) {
@@ -358,7 +375,7 @@ void Engine::tc_ensure_arena(int cap) {
     const auto& t = tensors_[i];
     const size_t tiles = big_[i] ? hr_sub_ : cap;
     const size_t elt = tc_fmt_[i] ? 2 * parts_ : 4;  // split tensors: hi tensor + lo tensor
-    if (parts_ == 2 && big_[i] && tc_fmt_[i]) continue;  // split mode never streams a 16-bit HR feature map through HBM
+    if (hr_simt_ && big_[i]) continue;  // high-resolution feature maps of the fp32 pair live in simt_buf_
     tbuf_[i].ensure((size_t)t.h * t.w * tc_cpad_[i] * elt * tiles);
   }
   for (size_t oi = 0; oi < ops_.size(); ++oi)
@@ -390,7 +407,7 @@ void Engine::tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float deno
     tc_run_fused(n, d_pred_m, max_depth, denom, s);
     return;
   }
-  if (parts_ == 2) {
+  if (hr_simt_) {
     run_hr_simt(n, d_pred_m, max_depth, denom, s);
     return;
   }
@@ -432,9 +449,10 @@ void Engine::tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float deno
   tbase_[ftid] = bufs[0];
 }
 
-// Split mode, high-resolution layers the fused split kernel does not cover (or FSR_X3_HR_SIMT=1, the A/B switch of the parity
-// tests): the low-resolution result is converted to fp32 NHWC and the layers run as plain fp32 FMA kernels (k_fp32.cu), a few
-// tiles at a time.  Correct for every graph the lowering accepts, far from the tensor-core roofline.
+// High-resolution layers the tensor-core kernels do not cover (widths other than 32, extra element-wise layers; in split mode also
+// FSR_X3_HR_SIMT=1, the A/B switch of the parity tests): the low-resolution result is converted to fp32 NHWC and the layers run
+// as plain fp32 FMA kernels (k_fp32.cu), a few tiles at a time.  Correct for every graph the lowering accepts, far from the
+// tensor-core roofline.
 void Engine::run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
   const int sub_tiles = 4;
   simt_buf_.resize(tensors_.size());
@@ -450,7 +468,7 @@ void Engine::run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, c
       simt_buf_[tid].ensure((size_t)cap_tiles_ * t.h * t.w * t.c * sizeof(float));
       ProfScope scope(prof, PROF_LR_MISC, s);
       launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(saved[tid]), simt_buf_[tid].as<float>(), n, t.h, t.w, tc_plane(tid), t.c, 1,
-                         tc_im_[tid], (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8, s);
+                         tc_im_[tid], parts_ == 2 ? (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8 : 0, s);
       tbase_[tid] = simt_buf_[tid].as<float>();
     }
     if (big_[op.dst] && (int)op.dst != hdr_.out_tensor) {
@@ -473,7 +491,7 @@ void Engine::run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, c
 
 void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int head_sms) {
   const float* W = d_weights_.as<float>();
-  const int half = precision_ != FSR_PREC_BF16 ? 1 : 0;
+  const int half = 1;
   const int parts = parts_;
   // elements between the hi and the lo tensor of a split CP8 tensor
   auto lo_off = [&](int tid) -> long long { return parts == 2 ? (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8 : 0; };
@@ -531,14 +549,13 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
       case FSR_OP_POOL:
         if (tc_fmt_[op.src0])
           launch_pool_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, op.mode, tc_plane(op.src0),
-                          tc_plane(op.dst), half, tc_im_[op.src0], tc_im_[op.dst], parts, s);
+                          tc_plane(op.dst), half, tc_im_[op.src0], tc_im_[op.dst], parts, op.aux, s);
         else
-          launch_pool_fp32(f32(op.src0), f32(op.dst), n, ts.h, ts.w, ts.c, op.k, op.mode, s);
+          launch_pool_fp32(f32(op.src0), f32(op.dst), n, ts.h, ts.w, ts.c, op.k, op.mode, op.aux, s);
         break;
       case FSR_OP_UPSAMPLE:
-        // a pure copy: the lo tensor of a split source is simply more planes
-        launch_upsample_cp8(cp8(op.src0), cp8(op.dst), parts * tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst),
-                            tc_im_[op.src0], tc_im_[op.dst], s);
+        launch_upsample_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst),
+                            tc_im_[op.src0], tc_im_[op.dst], op.mode, half, parts, s);
         break;
       case FSR_OP_ELTWISE: {
         // planes are strided by capacity: run plane by plane over the live pixels
@@ -546,8 +563,8 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
         const long long live = tc_im_[op.dst] ? tc_plane(op.dst) : (long long)n * td.h * td.w;
         for (int c8 = 0; c8 < tc_cpad_[op.dst] / 8; ++c8) {
           const size_t o = (size_t)c8 * tc_plane(op.dst) * 8;
-          launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, half,
-                             lo_off(op.dst) / 8, s);
+          launch_eltwise_cp8(cp8(op.src0) + o, op.src1 >= 0 ? cp8(op.src1) + o : nullptr, cp8(op.dst) + o, live, op.act, op.alpha, op.beta,
+                             half, lo_off(op.dst) / 8, s);
         }
         break;
       }
@@ -581,7 +598,7 @@ void Engine::debug_read_tensor(int tid, int n_tiles, float* d_out, cudaStream_t 
   const long long n_pix = (long long)n_tiles * t.h * t.w;
   if (precision_ != FSR_PREC_FP32_SIMT && tc_fmt_[tid]) {
     launch_cp8_to_nhwc(reinterpret_cast<const __nv_bfloat16*>(tbase_[tid]), d_out, n_tiles, t.h, t.w, tc_plane(tid), t.c,
-                       precision_ != FSR_PREC_BF16 ? 1 : 0, tc_im_[tid], parts_ == 2 ? (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8 : 0, s);
+                       1, tc_im_[tid], parts_ == 2 ? (long long)(tc_cpad_[tid] / 8) * tc_plane(tid) * 8 : 0, s);
   } else {
     FSR_CUDA(cudaMemcpyAsync(d_out, tbase_[tid], (size_t)n_pix * t.c * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }

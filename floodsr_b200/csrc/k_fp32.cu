@@ -140,7 +140,7 @@ __global__ void convt_fp32_kernel(const float* __restrict__ src, const float* __
 }
 
 __global__ void pool_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_img, int Hin, int Win, int C,
-                            int k, int mode) {
+                            int k, int mode, int aux) {
   const int Hout = Hin / k, Wout = Win / k;
   const size_t total = (size_t)n_img * Hout * Wout * C;
   const float inv = 1.0f / (float)(k * k);
@@ -151,6 +151,10 @@ __global__ void pool_kernel(const float* __restrict__ src, float* __restrict__ d
     size_t t2 = pix / Wout;
     int Y = (int)(t2 % Hout);
     size_t img = t2 / Hout;
+    if (mode == FSR_POOL_PICK) {
+      dst[idx] = __ldg(src + ((img * Hin + (size_t)Y * k + aux) * Win + (size_t)X * k + aux) * C + c);
+      continue;
+    }
     float acc = mode == 0 ? -INFINITY : 0.0f;
     for (int dy = 0; dy < k; ++dy)
       for (int dx = 0; dx < k; ++dx) {
@@ -162,7 +166,7 @@ __global__ void pool_kernel(const float* __restrict__ src, float* __restrict__ d
 }
 
 __global__ void upsample_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_img, int Hin, int Win, int C,
-                                int f) {
+                                int f, int mode) {
   const int Hout = Hin * f, Wout = Win * f;
   const size_t total = (size_t)n_img * Hout * Wout * C;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -172,15 +176,27 @@ __global__ void upsample_kernel(const float* __restrict__ src, float* __restrict
     size_t t2 = pix / Wout;
     int Y = (int)(t2 % Hout);
     size_t img = t2 / Hout;
-    dst[idx] = __ldg(src + ((img * Hin + Y / f) * Win + X / f) * C + c);
+    if (mode == FSR_UP_NEAREST) {
+      dst[idx] = __ldg(src + ((img * Hin + Y / f) * Win + X / f) * C + c);
+      continue;
+    }
+    int y0, y1, x0, x1;
+    float wy, wx;
+    up_linear_coord(Y, f, Hin, mode, y0, y1, wy);
+    up_linear_coord(X, f, Win, mode, x0, x1, wx);
+    const float* im = src + img * Hin * Win * C + c;
+    const float a = __ldg(im + ((size_t)y0 * Win + x0) * C), b = __ldg(im + ((size_t)y0 * Win + x1) * C);
+    const float d = __ldg(im + ((size_t)y1 * Win + x0) * C), e = __ldg(im + ((size_t)y1 * Win + x1) * C);
+    const float top = a + (b - a) * wx, bot = d + (e - d) * wx;
+    dst[idx] = top + (bot - top) * wy;
   }
 }
 
 __global__ void eltwise_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst,
-                               size_t total, int act, float alpha) {
+                               size_t total, int act, float alpha, float beta) {
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     float v = __ldg(a + idx) + (b ? __ldg(b + idx) : 0.0f);
-    dst[idx] = apply_act(v, act, alpha);
+    dst[idx] = apply_act2(v, act, alpha, beta);
   }
 }
 
@@ -234,20 +250,20 @@ void launch_convt_fp32(const float* src, const float* w, const float* bias, floa
   FSR_LAUNCH_CHECK();
 }
 
-void launch_pool_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int k, int mode, cudaStream_t s) {
+void launch_pool_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int k, int mode, int aux, cudaStream_t s) {
   size_t total = (size_t)n_img * (Hin / k) * (Win / k) * C;
-  pool_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, n_img, Hin, Win, C, k, mode);
+  pool_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, n_img, Hin, Win, C, k, mode, aux);
   FSR_LAUNCH_CHECK();
 }
 
-void launch_upsample_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int f, cudaStream_t s) {
+void launch_upsample_fp32(const float* src, float* dst, int n_img, int Hin, int Win, int C, int f, int mode, cudaStream_t s) {
   size_t total = (size_t)n_img * Hin * f * Win * f * C;
-  upsample_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, n_img, Hin, Win, C, f);
+  upsample_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, n_img, Hin, Win, C, f, mode);
   FSR_LAUNCH_CHECK();
 }
 
-void launch_eltwise_fp32(const float* a, const float* b, float* dst, size_t total, int act, float alpha, cudaStream_t s) {
-  eltwise_kernel<<<grid_for(total), 256, 0, s>>>(a, b, dst, total, act, alpha);
+void launch_eltwise_fp32(const float* a, const float* b, float* dst, size_t total, int act, float alpha, float beta, cudaStream_t s) {
+  eltwise_kernel<<<grid_for(total), 256, 0, s>>>(a, b, dst, total, act, alpha, beta);
   FSR_LAUNCH_CHECK();
 }
 

@@ -1,4 +1,4 @@
-// tcgen05 implicit-GEMM convolution for the low-resolution backbone (FSR_PREC_BF16) and the CP8 helper kernels.
+// tcgen05 implicit-GEMM convolution for the low-resolution backbone (FSR_PREC_FP16, and FSR_PREC_FP32 with split operands) and the CP8 helper kernels.
 //
 // Replaces ONNX Runtime's Conv kernels behind `session.run` (floodsr/engine/ort.py:193) for the ResUNet
 // encoder/decoder layers.  GEMM view: M = 128 output pixels (a bw x bh x bn box of the batched NHW grid),
@@ -700,7 +700,7 @@ __device__ __forceinline__ uint4 x8_max(const uint4& a, const uint4& b, int half
 // k x k pooling (stride k): one thread per (chunk, output pixel); source and destination may use different layouts
 __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
                                 int Hin, int Win, int k, int mode, long long ncap_in, long long ncap_out, int half, int im_in, int im_out,
-                                int parts) {
+                                int parts, int aux) {
   const int Hout = Hin / k, Wout = Win / k;
   const long long n_out = (long long)n_img * Hout * Wout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
@@ -723,6 +723,12 @@ __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bflo
     if (parts == 2) {
       // split tensors: pool the joined values (hi + lo is exact in fp32), then split again
       const long long lo_in = (long long)chunks * ncap_in * Hin * Win * 8, lo_out = (long long)chunks * ncap_out * Hout * Wout * 8;
+      if (mode == FSR_POOL_PICK) {
+        const long long a = chunk_off(im_in, ch, img, Y * k + aux, X * k + aux, Hin, Win, ncap_in);
+        *reinterpret_cast<uint4*>(dst + o) = __ldg(reinterpret_cast<const uint4*>(src + a));
+        *reinterpret_cast<uint4*>(dst + lo_out + o) = __ldg(reinterpret_cast<const uint4*>(src + lo_in + a));
+        continue;
+      }
       float acc[8];
       for (int dy = 0; dy < k; ++dy)
         for (int dx = 0; dx < k; ++dx) {
@@ -743,7 +749,9 @@ __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bflo
       *reinterpret_cast<uint4*>(dst + lo_out + o) = lo;
       continue;
     }
-    if (mode == 0) {
+    if (mode == FSR_POOL_PICK) {
+      *reinterpret_cast<uint4*>(dst + o) = __ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y * k + aux, X * k + aux, Hin, Win, ncap_in)));
+    } else if (mode == 0) {
       uint4 acc = __ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y * k, X * k, Hin, Win, ncap_in)));
       for (int dy = 0; dy < k; ++dy)
         for (int dx = 0; dx < k; ++dx)
@@ -766,8 +774,11 @@ __global__ void pool_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bflo
   }
 }
 
+// `chunks` counts the planes of ONE part; mode FSR_UP_NEAREST copies every part's planes, the bilinear modes interpolate the
+// (joined) values in fp32 and store them in the tensor's format again
 __global__ void upsample_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int chunks, int n_img,
-                                    int Hin, int Win, int f, long long ncap_in, long long ncap_out, int im_in, int im_out) {
+                                    int Hin, int Win, int f, long long ncap_in, long long ncap_out, int im_in, int im_out, int mode,
+                                    int half, int parts) {
   const int Hout = Hin * f, Wout = Win * f;
   const long long n_out = (long long)n_img * Hout * Wout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * chunks; i += (long long)gridDim.x * blockDim.x) {
@@ -786,13 +797,45 @@ __global__ void upsample_cp8_kernel(const __nv_bfloat16* __restrict__ src, __nv_
       Y = (int)(t2 % Hout);
       img = t2 / Hout;
     }
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + chunk_off(im_in, ch, img, Y / f, X / f, Hin, Win, ncap_in)));
-    *reinterpret_cast<uint4*>(dst + chunk_off(im_out, ch, img, Y, X, Hout, Wout, ncap_out)) = v;
+    const long long o = chunk_off(im_out, ch, img, Y, X, Hout, Wout, ncap_out);
+    const long long lo_in = (long long)chunks * ncap_in * Hin * Win * 8, lo_out = (long long)chunks * ncap_out * Hout * Wout * 8;
+    if (mode == FSR_UP_NEAREST) {
+      const long long a = chunk_off(im_in, ch, img, Y / f, X / f, Hin, Win, ncap_in);
+      *reinterpret_cast<uint4*>(dst + o) = __ldg(reinterpret_cast<const uint4*>(src + a));
+      if (parts == 2) *reinterpret_cast<uint4*>(dst + lo_out + o) = __ldg(reinterpret_cast<const uint4*>(src + lo_in + a));
+      continue;
+    }
+    int y0, y1, x0, x1;
+    float wy, wx;
+    up_linear_coord(Y, f, Hin, mode, y0, y1, wy);
+    up_linear_coord(X, f, Win, mode, x0, x1, wx);
+    float q[4][8];
+    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const long long a = chunk_off(im_in, ch, img, ys[t], xs[t], Hin, Win, ncap_in);
+      if (parts == 2) join_x8(__ldg(reinterpret_cast<const uint4*>(src + a)), __ldg(reinterpret_cast<const uint4*>(src + lo_in + a)), q[t]);
+      else unpack_x8(__ldg(reinterpret_cast<const uint4*>(src + a)), q[t], half);
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float top = q[0][j] + (q[1][j] - q[0][j]) * wx, bot = q[2][j] + (q[3][j] - q[2][j]) * wx;
+      r[j] = top + (bot - top) * wy;
+    }
+    if (parts == 2) {
+      uint4 hi, lo;
+      split_x8(r, hi, lo);
+      *reinterpret_cast<uint4*>(dst + o) = hi;
+      *reinterpret_cast<uint4*>(dst + lo_out + o) = lo;
+    } else {
+      *reinterpret_cast<uint4*>(dst + o) = pack_x8(r, half);
+    }
   }
 }
 
 __global__ void eltwise_cp8_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                   __nv_bfloat16* __restrict__ dst, long long n_vec, int act, float alpha, int half, long long lo_vec) {
+                                   __nv_bfloat16* __restrict__ dst, long long n_vec, int act, float alpha, float beta, int half, long long lo_vec) {
   // lo_vec != 0: split tensors, the lo part lies lo_vec 16-byte vectors behind the hi part
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
@@ -805,7 +848,7 @@ __global__ void eltwise_cp8_kernel(const __nv_bfloat16* __restrict__ a, const __
       for (int j = 0; j < 8; ++j) x[j] += y[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], act, alpha);
+    for (int j = 0; j < 8; ++j) x[j] = apply_act2(x[j], act, alpha, beta);
     if (lo_vec) {
       uint4 hi, lo;
       split_x8(x, hi, lo);
@@ -1118,24 +1161,24 @@ void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bf
 }
 
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
-                     long long plane_in, long long plane_out, int half, int im_in, int im_out, int parts, cudaStream_t s) {
+                     long long plane_in, long long plane_out, int half, int im_in, int im_out, int parts, int aux, cudaStream_t s) {
   const long long ncap_in = plane_in / ((long long)Hin * Win), ncap_out = plane_out / ((long long)(Hin / k) * (Win / k));
   pool_cp8_kernel<<<grid_for((long long)n_img * (Hin / k) * (Win / k) * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, k, mode,
-                                                                                                ncap_in, ncap_out, half, im_in, im_out, parts);
+                                                                                                ncap_in, ncap_out, half, im_in, im_out, parts, aux);
   FSR_LAUNCH_CHECK();
 }
 
 void launch_upsample_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int f,
-                         long long plane_in, long long plane_out, int im_in, int im_out, cudaStream_t s) {
+                         long long plane_in, long long plane_out, int im_in, int im_out, int mode, int half, int parts, cudaStream_t s) {
   const long long ncap_in = plane_in / ((long long)Hin * Win), ncap_out = plane_out / ((long long)Hin * f * Win * f);
   upsample_cp8_kernel<<<grid_for((long long)n_img * Hin * f * Win * f * chunks), 256, 0, s>>>(src, dst, chunks, n_img, Hin, Win, f,
-                                                                                                ncap_in, ncap_out, im_in, im_out);
+                                                                                                ncap_in, ncap_out, im_in, im_out, mode, half, parts);
   FSR_LAUNCH_CHECK();
 }
 
 void launch_eltwise_cp8(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* dst, long long n_vec, int act, float alpha,
-                        int half, long long lo_vec, cudaStream_t s) {
-  eltwise_cp8_kernel<<<grid_for(n_vec), 256, 0, s>>>(a, b, dst, n_vec, act, alpha, half, lo_vec);
+                        float beta, int half, long long lo_vec, cudaStream_t s) {
+  eltwise_cp8_kernel<<<grid_for(n_vec), 256, 0, s>>>(a, b, dst, n_vec, act, alpha, beta, half, lo_vec);
   FSR_LAUNCH_CHECK();
 }
 

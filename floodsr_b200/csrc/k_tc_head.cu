@@ -1,4 +1,4 @@
-// tcgen05 kernels for the high-resolution end of the network (FSR_PREC_BF16): the 16x transposed
+// tcgen05 kernels for the high-resolution end of the network (FSR_PREC_FP16, graphs the fused kernel does not cover): the 16x transposed
 // convolution and the fused head (conv3x3 over concat(features, dem_hr) -> act -> conv1x1 -> log1p inversion).
 // Together they are ~90 % of the FLOPs behind `session.run` (floodsr/engine/ort.py:193) and the
 // invert_depth_log1p_np call that follows it (ort.py:196, preprocessing.py:154-164).

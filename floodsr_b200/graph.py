@@ -27,9 +27,11 @@ import numpy as np
 from floodsr_b200.onnx_io import OnnxModel, OnnxNode, load_onnx
 
 PLAN_MAGIC = 0x50525346
-PLAN_VERSION = 1
+PLAN_VERSION = 2
 OP_CONV, OP_POOL, OP_UPSAMPLE, OP_CONVT, OP_ELTWISE, OP_HEAD = 1, 2, 3, 4, 5, 6
-ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_CLIP, ACT_SIGMOID = 0, 1, 2, 3, 4  # CLIP / SIGMOID only on ELTWISE ops
+POOL_MAX, POOL_AVG, POOL_PICK = 0, 1, 2  # PICK: element (aux, aux) of every k x k block (a strided convolution's sampling)
+UP_NEAREST, UP_LINEAR_HALF_PIXEL, UP_LINEAR_ALIGN_CORNERS, UP_LINEAR_ASYMMETRIC = 0, 1, 2, 3
 _OP_NAMES = {1: "CONV", 2: "POOL", 3: "UPSAMPLE", 4: "CONVT", 5: "ELTWISE", 6: "HEAD"}
 
 
@@ -44,7 +46,9 @@ class PlanOp:
     mode: int = 0
     cout: int = 0
     act: int = ACT_NONE
-    alpha: float = 0.0
+    alpha: float = 0.0                # LEAKY slope / CLIP lower bound
+    beta: float = 0.0                 # CLIP upper bound
+    aux: int = 0                      # POOL_PICK: offset inside the block
     weight: np.ndarray | None = None  # HWIO
     bias: np.ndarray | None = None
     weight2: np.ndarray | None = None  # HEAD 1x1 [cmid]
@@ -147,6 +151,8 @@ class _Val:
     tids: list[int]
     layout: str  # "NHWC" | "NCHW"
     producer: int = -1  # index into ops of the op that wrote tids[0] (single-tensor values only)
+    pad: tuple[int, int, int, int] = (0, 0, 0, 0)  # pending zero padding (top, left, bottom, right) from a Pad node, consumed by
+                                                   # the convolution that follows (tf2onnx emits SAME padding of strided convs so)
 
 
 class _Lowering:
@@ -176,6 +182,8 @@ class _Lowering:
         name = node.inputs[idx]
         if name not in self.vals:
             self.fail(node, f"input '{name}' is not an activation tensor")
+        if any(self.vals[name].pad) and node.op_type != "Conv":
+            self.fail(node, "a Pad node must be followed by the convolution it pads")
         return self.vals[name]
 
     def single(self, node: OnnxNode, v: _Val) -> int:
@@ -183,12 +191,17 @@ class _Lowering:
             self.fail(node, "channel Concat feeding this operator would have to be materialised")
         return v.tids[0]
 
-    def fusable_producer(self, name: str, kinds=(OP_CONV, OP_CONVT, OP_ELTWISE)) -> PlanOp | None:
-        """The op that produced ONNX value `name`, if later nodes may still be folded into it."""
+    def fusable_producer(self, name: str, kinds=(OP_CONV, OP_CONVT, OP_ELTWISE), through_pick: bool = True) -> PlanOp | None:
+        """The op that produced ONNX value `name`, if later nodes may still be folded into it.
+
+        Pointwise followers (activation, per-channel scale / bias) commute with the element picking of a strided
+        convolution, so they fold into the convolution in front of its POOL_PICK (`through_pick`)."""
         v = self.vals.get(name)
         if v is None or len(v.tids) != 1 or v.producer < 0 or self.uses.get(name, 0) != 1:
             return None
         op = self.ops[v.producer]
+        if through_pick and op.kind == OP_POOL and op.mode == POOL_PICK and v.producer >= 1 and self.ops[v.producer - 1].dst == op.src0:
+            op = self.ops[v.producer - 1]
         return op if op.kind in kinds else None
 
     # -- node handlers ---------------------------------------------------------------------------
@@ -252,18 +265,41 @@ class _Lowering:
             self.fail(node, "weights must be a rank-4 initializer")
         cout, cin, kh, kw = w.shape
         a = node.attrs
-        if a.get("group", 1) != 1 or kh != kw or kh not in (1, 3) or list(a.get("strides", [1, 1])) != [1, 1]:
-            self.fail(node, "only group=1, stride-1, 1x1 or 3x3 convolutions are supported")
+        strides = list(a.get("strides", [1, 1]))
+        if a.get("group", 1) != 1 or kh != kw or kh not in (1, 3) or strides[0] != strides[1] or strides[0] not in (1, 2):
+            self.fail(node, "only group=1, 1x1 or 3x3 convolutions with stride 1 or 2 are supported")
         if list(a.get("dilations", [1, 1])) != [1, 1]:
             self.fail(node, "dilated convolution")
-        pads = list(a.get("pads", [0, 0, 0, 0]))
+        st = int(strides[0])
+        h, wd, _ = self.tensors[v.tids[0]]
+        # total padding = the node's own (pads / auto_pad) + what a preceding Pad node left pending on the value
         auto = a.get("auto_pad", "NOTSET")
-        if not (pads == [kh // 2] * 4 or auto in ("SAME_UPPER", "SAME_LOWER")):
-            self.fail(node, f"only 'same' padding is supported (pads={pads}, auto_pad={auto})")
+        if auto in ("SAME_UPPER", "SAME_LOWER"):
+            own = []
+            for size in (h, wd):
+                total = max((-(-size // st) - 1) * st + kh - size, 0)
+                lo = total // 2 if auto == "SAME_UPPER" else total - total // 2
+                own.append((lo, total - lo))
+            pads = [own[0][0], own[1][0], own[0][1], own[1][1]]
+        elif auto == "VALID":
+            pads = [0, 0, 0, 0]
+        else:
+            pads = [int(x) for x in a.get("pads", [0, 0, 0, 0])]
+        pt, pl, pb, pr = (pads[i] + v.pad[i] for i in range(4))
+        # A stride-s convolution samples the stride-1 'same' convolution at rows pt' + s*i where pt' = k//2 - pt is how far the
+        # first window's centre sits from row 0: lowered as CONV (stride 1, same padding) + POOL_PICK(k = s, offset pt').
+        half = kh // 2
+        off_y, off_x = half - pt, half - pl
+        out_h = (h + pt + pb - kh) // st + 1
+        out_w = (wd + pl + pr - kh) // st + 1
+        ok = off_y == off_x and 0 <= off_y < st and out_h * st == h and out_w * st == wd
+        if st == 1:
+            ok = (pt, pl, pb, pr) == (half, half, half, half)
+        if not ok:
+            self.fail(node, f"padding {(pt, pl, pb, pr)} with stride {st} is not a 'same' convolution of the {h}x{wd} map")
         cin_have = sum(self.tensors[t][2] for t in v.tids)
         if cin_have != cin:
             self.fail(node, f"weight expects {cin} input channels, activation has {cin_have}")
-        h, wd, _ = self.tensors[v.tids[0]]
         bias = None
         if len(node.inputs) > 2 and node.inputs[2]:
             bias = np.asarray(self.consts[node.inputs[2]], dtype=np.float32).reshape(cout)
@@ -274,7 +310,33 @@ class _Lowering:
             name=node.name or node.outputs[0],
         )
         self.ops.append(op)
-        self.vals[node.outputs[0]] = _Val([dst], "NCHW", len(self.ops) - 1)
+        if st == 1:
+            self.vals[node.outputs[0]] = _Val([dst], "NCHW", len(self.ops) - 1)
+            return
+        # a value that is sampled afterwards can take no later fusion (activation, residual) before the sampling: those
+        # commute with picking elements, so they are applied to the small tensor by ELTWISE ops if they follow
+        small = self.new_tensor(h // st, wd // st, cout)
+        self.ops.append(PlanOp(OP_POOL, src0=dst, dst=small, k=st, mode=POOL_PICK, aux=int(off_y), name=(node.name or node.outputs[0]) + "/stride"))
+        self.vals[node.outputs[0]] = _Val([small], "NCHW", len(self.ops) - 1)
+
+    def n_Pad(self, node: OnnxNode):
+        v = self.act_in(node)
+        self._check_nchw(node, v)
+        pads = self.consts.get(node.inputs[1]) if len(node.inputs) > 1 and node.inputs[1] else node.attrs.get("pads")
+        if pads is None:
+            self.fail(node, "Pad needs constant pads")
+        p = [int(x) for x in np.asarray(pads).reshape(-1)]
+        value = 0.0
+        if len(node.inputs) > 2 and node.inputs[2]:
+            cv = self.consts.get(node.inputs[2])
+            value = float(np.asarray(cv).reshape(-1)[0]) if cv is not None and np.asarray(cv).size else 0.0
+        elif "value" in node.attrs:
+            value = float(node.attrs["value"])
+        if node.attrs.get("mode", "constant") != "constant" or value != 0.0 or len(p) != 8 or p[0] or p[1] or p[4] or p[5]:
+            self.fail(node, "only zero-valued spatial Pad is supported")
+        if any(x < 0 for x in p) or self.uses.get(node.outputs[0], 0) != 1:
+            self.fail(node, "Pad must be non-negative and feed exactly one convolution")
+        self.vals[node.outputs[0]] = _Val(v.tids, v.layout, -1, (v.pad[0] + p[2], v.pad[1] + p[3], v.pad[2] + p[6], v.pad[3] + p[7]))
 
     def n_ConvTranspose(self, node: OnnxNode):
         v = self.act_in(node)
@@ -327,6 +389,92 @@ class _Lowering:
         self.ops.append(PlanOp(OP_ELTWISE, src0=src, dst=dst, act=act, alpha=float(alpha), name=node.name))
         self.vals[node.outputs[0]] = _Val([dst], v.layout, len(self.ops) - 1)
 
+    def _pointwise(self, node: OnnxNode, act: int, alpha: float, beta: float):
+        """Activations the convolution epilogues do not implement: a separate element-wise pass."""
+        v = self.act_in(node)
+        src = self.single(node, v)
+        dst = self.new_tensor(*self.tensors[src])
+        self.ops.append(PlanOp(OP_ELTWISE, src0=src, dst=dst, act=act, alpha=float(alpha), beta=float(beta), name=node.name))
+        self.vals[node.outputs[0]] = _Val([dst], v.layout, len(self.ops) - 1)
+
+    def n_Sigmoid(self, node: OnnxNode):
+        self._pointwise(node, ACT_SIGMOID, 0.0, 0.0)
+
+    def n_Clip(self, node: OnnxNode):
+        def bound(i, key, default):
+            if len(node.inputs) > i and node.inputs[i]:
+                c = self.consts.get(node.inputs[i])
+                if c is None:
+                    self.fail(node, "Clip bounds must be constants")
+                return float(np.asarray(c).reshape(-1)[0])
+            return float(node.attrs.get(key, default))
+
+        lo, hi = bound(1, "min", -3.4028234663852886e38), bound(2, "max", 3.4028234663852886e38)
+        if lo == 0.0 and hi >= 3.0e38:
+            self._activation(node, ACT_RELU)  # Clip(0, +inf) is how some exporters write Relu
+        else:
+            self._pointwise(node, ACT_CLIP, lo, hi)
+
+    def _scale_shift(self, node: OnnxNode, kind: str):
+        """Mul / Div / Sub by a per-channel (or scalar) constant right after a convolution: folded into its weights and bias
+        (an unfolded BatchNormalization looks like this).  `const - x` and `const / x` are not affine in the weights."""
+        a_name, b_name = node.inputs[0], node.inputs[1]
+        if b_name in self.consts and a_name in self.vals:
+            act_name, cst = a_name, self.consts[b_name]
+        elif a_name in self.consts and b_name in self.vals and kind == "Mul":
+            act_name, cst = b_name, self.consts[a_name]
+        else:
+            self.fail(node, f"{kind} needs (activation, constant) operands")
+        prod = self.fusable_producer(act_name, kinds=(OP_CONV, OP_CONVT))
+        c = np.asarray(cst, np.float64).reshape(-1)
+        if prod is None or prod.act != ACT_NONE or prod.res >= 0 or c.size not in (1, prod.cout):
+            self.fail(node, f"constant {kind} that is not a per-channel scale / shift right after a convolution")
+        c = np.broadcast_to(c, (prod.cout,))
+        if kind == "Sub":
+            b0 = prod.bias.astype(np.float64) if prod.bias is not None else np.zeros(prod.cout)
+            prod.bias = (b0 - c).astype(np.float32)
+        else:
+            g = c if kind == "Mul" else 1.0 / c
+            prod.weight = (prod.weight.astype(np.float64) * g.reshape(1, 1, 1, -1)).astype(np.float32)
+            if prod.bias is not None:
+                prod.bias = (prod.bias.astype(np.float64) * g).astype(np.float32)
+        self.vals[node.outputs[0]] = self.vals[act_name]
+
+    def n_Mul(self, node: OnnxNode):
+        self._scale_shift(node, "Mul")
+
+    def n_Div(self, node: OnnxNode):
+        self._scale_shift(node, "Div")
+
+    def n_Sub(self, node: OnnxNode):
+        self._scale_shift(node, "Sub")
+
+    def _same_shape_view(self, node: OnnxNode, target: list[int] | None):
+        """Reshape / Squeeze / Unsqueeze / Cast / Flatten-like nodes that leave a 4-D activation exactly as it is."""
+        v = self.act_in(node)
+        t = self.single(node, v)
+        h, w, c = self.tensors[t]
+        cur = [c, h, w] if v.layout == "NCHW" else [h, w, c]
+        if target is not None:
+            tgt = [int(x) for x in target]
+            if len(tgt) != 4 or [cur[i] if x == 0 else x for i, x in enumerate(tgt[1:])] != cur or tgt[0] not in (0, -1, 1):
+                self.fail(node, f"reshape of a {v.layout} {cur} activation to {tgt} changes its layout")
+        self.vals[node.outputs[0]] = v
+
+    def n_Reshape(self, node: OnnxNode):
+        shape = self.consts.get(node.inputs[1]) if len(node.inputs) > 1 else None
+        if shape is None:
+            self.fail(node, "Reshape needs a constant shape")
+        self._same_shape_view(node, list(np.asarray(shape).reshape(-1)))
+
+    def n_Cast(self, node: OnnxNode):
+        if int(node.attrs.get("to", 1)) != 1:
+            self.fail(node, "only casts to float32 are supported")
+        if node.inputs[0] in self.consts:
+            self.consts[node.outputs[0]] = np.asarray(self.consts[node.inputs[0]], np.float32)
+        else:
+            self._same_shape_view(node, None)
+
     def n_Relu(self, node: OnnxNode):
         self._activation(node, ACT_RELU)
 
@@ -356,7 +504,7 @@ class _Lowering:
             return next((i for i, op in enumerate(self.ops) if op.dst == tid), -1)  # graph inputs: -1
 
         for mine, other, v in ((a_name, tb, va), (b_name, ta, vb)):
-            prod = self.fusable_producer(mine, kinds=(OP_CONV,))
+            prod = self.fusable_producer(mine, kinds=(OP_CONV,), through_pick=False)
             if prod is not None and prod.act == ACT_NONE and prod.res < 0 and born(other) < v.producer:
                 prod.res = other
                 self.vals[node.outputs[0]] = _Val(v.tids, v.layout, v.producer)
@@ -406,8 +554,21 @@ class _Lowering:
         self._check_nchw(node, v)
         src = self.single(node, v)
         h, w, c = self.tensors[src]
-        if node.attrs.get("mode", "nearest") != "nearest":
-            self.fail(node, "only nearest-neighbour upsampling is supported")
+        mode = node.attrs.get("mode", "nearest")
+        if isinstance(mode, bytes):
+            mode = mode.decode()
+        ctm = node.attrs.get("coordinate_transformation_mode", "half_pixel")
+        if isinstance(ctm, bytes):
+            ctm = ctm.decode()
+        if mode == "nearest":
+            up_mode = UP_NEAREST  # integer factors: asymmetric/floor and half_pixel/round_prefer_floor pick the same source pixel
+        elif mode in ("linear", "bilinear"):
+            up_mode = {"half_pixel": UP_LINEAR_HALF_PIXEL, "pytorch_half_pixel": UP_LINEAR_HALF_PIXEL,
+                       "align_corners": UP_LINEAR_ALIGN_CORNERS, "asymmetric": UP_LINEAR_ASYMMETRIC}.get(ctm)
+            if up_mode is None:
+                self.fail(node, f"linear Resize with coordinate_transformation_mode={ctm}")
+        else:
+            self.fail(node, f"Resize mode '{mode}' is not supported")
         if scales is not None and scales.size == 4:
             sc = [float(x) for x in scales.reshape(-1)]
         elif sizes is not None and sizes.size == 4:
@@ -419,7 +580,7 @@ class _Lowering:
             self.fail(node, f"only integer spatial upsampling is supported (scales={sc})")
         f = int(sc[2])
         dst = self.new_tensor(h * f, w * f, c)
-        self.ops.append(PlanOp(OP_UPSAMPLE, src0=src, dst=dst, k=f, name=node.name))
+        self.ops.append(PlanOp(OP_UPSAMPLE, src0=src, dst=dst, k=f, mode=up_mode, name=node.name))
         self.vals[node.outputs[0]] = _Val([dst], "NCHW", len(self.ops) - 1)
 
     def n_Resize(self, node: OnnxNode):
@@ -482,8 +643,8 @@ def _serialise(lm: LoweredModel) -> None:
     for op in lm.ops:
         w_off, b_off, w2_off, b2_off = put(op.weight), put(op.bias), put(op.weight2), put(op.bias2)
         out += struct.pack(
-            "<9if6i", op.kind, op.src0, op.src1, op.res, op.dst, op.k, op.mode, op.cout, op.act, op.alpha,
-            w_off, b_off, w2_off, b2_off, 0, 0,
+            "<9if4ifi", op.kind, op.src0, op.src1, op.res, op.dst, op.k, op.mode, op.cout, op.act, op.alpha,
+            w_off, b_off, w2_off, b2_off, op.beta, op.aux,
         )
     lm.plan_bytes = bytes(out)
     lm.weights = np.concatenate(blobs) if blobs else np.zeros(0, np.float32)

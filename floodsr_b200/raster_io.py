@@ -154,7 +154,9 @@ def write_geotiff(fp, array: np.ndarray, transform, nodata=None, geo_tags: dict 
             ifd[tag] = geo_tags[tag]
             ifd.tagtype[tag] = kind
     if nodata is not None:
-        ifd[TAG_GDAL_NODATA] = repr(float(nodata)) if float(nodata) != int(nodata) else str(int(nodata))
+        v = float(nodata)  # GDAL_NODATA is ASCII: "nan", "inf", "-inf" are legal and common for float DEMs
+        ifd[TAG_GDAL_NODATA] = ("nan" if math.isnan(v) else ("inf" if v > 0 else "-inf")) if not math.isfinite(v) else (
+            str(int(v)) if v.is_integer() else repr(v))
         ifd.tagtype[TAG_GDAL_NODATA] = TiffTags.ASCII
     Image.fromarray(arr, mode="F").save(path, format="TIFF", compression=compression, tiffinfo=ifd)
     return path

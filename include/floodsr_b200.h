@@ -40,8 +40,9 @@ extern "C" {
 /* precision modes of the network forward pass */
 #define FSR_PREC_FP32 0 /* fp32-tolerance mode (<=1e-4 m vs the fp32 oracle) on tcgen05 tensor cores: every activation and
                            weight is a split fp16 pair (hi, lo), three MMAs per product, fp32 accumulate in TMEM      */
-#define FSR_PREC_BF16 1 /* tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM     */
-#define FSR_PREC_FP16 2 /* same kernels with fp16 operands/activations (3 more mantissa bits)  */
+/* 1 was bf16 operands: measured 2.4e-2 m on the H1 graph, outside the <=1e-2 m bound of the 16-bit mode; retired, fsr_create rejects it */
+#define FSR_PREC_FP16 2 /* the 16-bit tensor-core mode (<=1e-2 m, same wet/dry mask at 0.01 m): tcgen05 kind::f16, fp16
+                           operands and activations, fp32 accumulate in TMEM                                            */
 #define FSR_PREC_FP32_SIMT 3 /* diagnostic: plain fp32 FMA on the CUDA cores (independent check of the tensor-core modes) */
 
 /* window methods of the tile loop (floodsr/models/ResUNet_16x_DEM.py:297, :315) */
@@ -205,8 +206,8 @@ int fsr_profile_enable(fsr_engine* eng, int32_t on);
 int fsr_profile_fetch(fsr_engine* eng, double* out_ms, int64_t* out_count, int32_t n_cat);
 
 /* ---- debugging: read an intermediate activation of the last forward pass as NHWC float32 ------------------
- * (first n_tiles tiles of the last chunk; bf16 CP8 tensors are converted).  Used by layer-by-layer parity
- * tests between the fp32 and bf16 backends. */
+ * (first n_tiles tiles of the last chunk; 16-bit and split CP8 tensors are converted).  Used by the layer-by-layer error
+ * budget of the precision modes (tests/x3_error_budget.py). */
 int fsr_debug_tensor_shape(fsr_engine* eng, int32_t tensor, int32_t* h, int32_t* w, int32_t* c);
 int fsr_debug_read_tensor(fsr_engine* eng, int32_t tensor, int32_t n_tiles, float* out);
 

@@ -262,6 +262,18 @@ def _op_resize(x, roi=None, scales=None, sizes=None, **a):
     if mode == "linear":
         if ctm == "align_corners":
             return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+        if ctm == "asymmetric":
+            # ONNX Resize: x_original = x_resized / scale; weights from the fractional part, upper neighbour clamped
+            out = x
+            for dim, n_out in ((2, size[0]), (3, size[1])):
+                n_in = out.shape[dim]
+                pos = torch.arange(n_out, dtype=out.dtype) * (n_in / n_out)
+                i0 = pos.floor().long().clamp(max=n_in - 1)
+                i1 = (i0 + 1).clamp(max=n_in - 1)
+                w1 = (pos - i0).view([-1 if d == dim else 1 for d in range(4)])
+                lo, hi = out.index_select(dim, i0), out.index_select(dim, i1)
+                out = lo + (hi - lo) * w1
+            return out
         assert ctm in ("half_pixel", "pytorch_half_pixel"), f"linear Resize ctm={ctm} not supported"
         return F.interpolate(x, size=size, mode="bilinear", align_corners=False)
     raise NotImplementedError(f"Resize mode {mode}")
@@ -338,6 +350,7 @@ _OPS = {
     "Reshape": _op_reshape,
     "Squeeze": _op_squeeze,
     "Unsqueeze": _op_unsqueeze,
+    "Cast": lambda x, **a: x.to(torch.float32) if int(a.get("to", 1)) == 1 else x,
 }
 
 

@@ -18,6 +18,10 @@ def _act(x, op):
         return torch.relu(x)
     if op.act == G.ACT_LEAKY:
         return F.leaky_relu(x, op.alpha)
+    if op.act == G.ACT_CLIP:
+        return torch.clamp(x, op.alpha, op.beta)
+    if op.act == G.ACT_SIGMOID:
+        return torch.sigmoid(x)
     return x
 
 
@@ -26,6 +30,32 @@ def _conv(x_nhwc, w_hwio, bias, k):
     w = torch.from_numpy(np.ascontiguousarray(w_hwio)).permute(3, 2, 0, 1).to(x.dtype)
     b = torch.from_numpy(bias).to(x.dtype) if bias is not None else None
     return F.conv2d(x, w, b, padding=k // 2).permute(0, 2, 3, 1)
+
+
+def _bilinear(x_nhwc, f, mode):
+    """The engine's bilinear upsampling (fsr_common.cuh: up_linear_coord), written out with explicit gathers."""
+    n, h, w, c = x_nhwc.shape
+
+    def coords(n_in):
+        o = torch.arange(n_in * f, dtype=x_nhwc.dtype)
+        if mode == G.UP_LINEAR_ALIGN_CORNERS:
+            x = o * (n_in - 1) / (n_in * f - 1) if n_in * f > 1 else o * 0
+        elif mode == G.UP_LINEAR_ASYMMETRIC:
+            x = o / f
+        else:
+            x = (o + 0.5) / f - 0.5
+        x = x.clamp(0, n_in - 1)
+        i0 = x.floor().long()
+        i1 = (i0 + 1).clamp(max=n_in - 1)
+        return i0, i1, (x - i0)
+
+    y0, y1, wy = coords(h)
+    x0, x1, wx = coords(w)
+    wy, wx = wy.view(1, -1, 1, 1), wx.view(1, 1, -1, 1)
+    rows0, rows1 = x_nhwc[:, y0], x_nhwc[:, y1]
+    top = rows0[:, :, x0] + (rows0[:, :, x1] - rows0[:, :, x0]) * wx
+    bot = rows1[:, :, x0] + (rows1[:, :, x1] - rows1[:, :, x0]) * wx
+    return top + (bot - top) * wy
 
 
 def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray, dtype=torch.float32, return_all: bool = False):
@@ -50,9 +80,15 @@ def run_plan(lm: G.LoweredModel, depth_norm: np.ndarray, dem_norm: np.ndarray, d
                         y = y + float(op.bias2.reshape(-1)[0])
             elif op.kind == G.OP_POOL:
                 x = t[op.src0].permute(0, 3, 1, 2)
-                y = (F.max_pool2d(x, op.k) if op.mode == 0 else F.avg_pool2d(x, op.k)).permute(0, 2, 3, 1)
+                if op.mode == G.POOL_PICK:
+                    y = x[:, :, op.aux :: op.k, op.aux :: op.k].permute(0, 2, 3, 1)
+                else:
+                    y = (F.max_pool2d(x, op.k) if op.mode == 0 else F.avg_pool2d(x, op.k)).permute(0, 2, 3, 1)
             elif op.kind == G.OP_UPSAMPLE:
-                y = t[op.src0].repeat_interleave(op.k, dim=1).repeat_interleave(op.k, dim=2)
+                if op.mode == G.UP_NEAREST:
+                    y = t[op.src0].repeat_interleave(op.k, dim=1).repeat_interleave(op.k, dim=2)
+                else:
+                    y = _bilinear(t[op.src0], op.k, op.mode)
             elif op.kind == G.OP_CONVT:
                 x = t[op.src0].permute(0, 3, 1, 2)
                 w = torch.from_numpy(np.ascontiguousarray(op.weight)).permute(2, 3, 0, 1).to(dtype)  # [kh,kw,ci,co] -> [ci,co,kh,kw]

@@ -313,6 +313,64 @@ def test_run_raster_properties_at_mersch_size(engine):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# graphs other than H1: operator spellings of a tf2onnx export, other widths (the loader runs whatever the file holds)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _engine_vs_oracle_on_model(fp, precision, tol_norm, seeds=(3, 4)):
+    from floodsr_b200.engine import EngineB200
+    from oracle import preprocessing_np as pp
+    from oracle.engine_ref import OracleEngine
+
+    dn = np.stack([pp.scale_depth_log1p(synth_depth(32, 32, seed=s), 5.0) for s in seeds])
+    en = np.stack([pp.normalize_dem(synth_dem(512, 512, seed=s))[0] for s in seeds])
+    want = OracleEngine(fp).forward_norm(dn, en)
+    eng = EngineB200(fp, precision=precision)
+    got = eng.stage_forward(dn, en)
+    eng.close()
+    assert want.std() > 1e-3
+    err = float(np.abs(got - want).max())
+    assert err <= tol_norm, (precision, err)
+    return err
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp16", 4e-3), ("fp32_simt", 1e-5)])
+def test_export_spelling_variants_on_the_engine(tmp_path, precision, tol):
+    """Pad + VALID conv, stride-2 convs (both padding conventions), bilinear Resize (half_pixel and align_corners), unfolded
+    normalisation (Mul / Sub / Div), Clip, Sigmoid, Reshape / Cast -- all in one graph, against the oracle's interpreter."""
+    from floodsr_b200.onnx_io import save_onnx
+    from tests import h1_variants as V
+
+    fp = tmp_path / "everything.onnx"
+    save_onnx(V.everything(), fp)
+    _engine_vs_oracle_on_model(fp, precision, tol)
+
+
+@pytest.mark.parametrize("ctm", ["asymmetric"])
+def test_bilinear_asymmetric_resize_on_the_engine(tmp_path, ctm):
+    from floodsr_b200.h1 import build_h1_model
+    from floodsr_b200.onnx_io import save_onnx
+    from tests import h1_variants as V
+
+    fp = tmp_path / "bilinear.onnx"
+    save_onnx(V.bilinear_resize(build_h1_model(seed=6), ctm, which=(0, 1, 2, 3)), fp)
+    _engine_vs_oracle_on_model(fp, "fp32", 1e-5)
+
+
+@pytest.mark.parametrize("f", [16, 64])
+def test_other_widths_run_with_the_fp32_high_resolution_pair(tmp_path, f):
+    """base_filters 16 / 64: the low-resolution layers stay on tcgen05 (16-channel outputs, 1024-channel deep level), the
+    high-resolution end (not 32 channels) runs on the fp32 FMA kernels -- in both tensor-core modes."""
+    from floodsr_b200.h1 import build_h1_model
+    from floodsr_b200.onnx_io import save_onnx
+
+    fp = tmp_path / f"h1_f{f}.onnx"
+    save_onnx(build_h1_model(seed=2, base_filters=f), fp)
+    _engine_vs_oracle_on_model(fp, "fp32", 1e-5, seeds=(3,))
+    _engine_vs_oracle_on_model(fp, "fp16", 4e-3, seeds=(3,))
+
+
+# ---------------------------------------------------------------------------------------------------------
 # BASELINE configs 2-4 against the oracle's tile loop (oracle/stitch_np.run_tiled over the torch-CPU network)
 # ---------------------------------------------------------------------------------------------------------
 
@@ -433,19 +491,18 @@ def test_band_sharding_is_bit_identical_to_single_pass(engine, h, w, world, spli
 
 
 # ---------------------------------------------------------------------------------------------------------
-# tensor-core modes (tcgen05, bf16 / fp16 operands, fp32 accumulate): north-star tolerance 1e-2 m and the same
+# the 16-bit tensor-core mode (tcgen05, fp16 operands, fp32 accumulate): north-star tolerance 1e-2 m and the same
 # wet/dry mask at a 0.01 m threshold
 # ---------------------------------------------------------------------------------------------------------
 
-# fp16 operands meet the north-star bound (1e-2 m); bf16 operands (3 fewer mantissa bits) are measured at ~2.5e-2 m on
-# the random-init H1 graph, i.e. they do NOT meet it here: the bound below only guards against regressions and
-# DESIGN.md states the measured figure.
-TC_TOL_M = {"fp16": 1e-2, "bf16": 5e-2}
-TC_TOL_NORM = {"fp16": 2e-3, "bf16": 1e-2}
+# fp16 operands meet the north-star bound of the 16-bit mode (1e-2 m).  bf16 operands (3 fewer mantissa bits) measured
+# 2.4e-2 m on the H1 graph in round 1, i.e. outside the bound: that mode was retired instead of tested against a looser one.
+TC_TOL_M = {"fp16": 1e-2}
+TC_TOL_NORM = {"fp16": 2e-3}
 WET_M = 0.01
 
 
-@pytest.fixture(scope="module", params=["bf16", "fp16"])
+@pytest.fixture(scope="module", params=["fp16"])
 def tc_engine(request, h1_model_fp):
     from floodsr_b200.engine import EngineB200
 

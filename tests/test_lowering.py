@@ -164,3 +164,65 @@ def test_garbage_file_is_rejected(tmp_path):
     fp.write_text("dummy onnx placeholder\n")  # the reference's 23-byte stub (tests/data/model_infer_dummy.onnx)
     with pytest.raises((ValueError, AssertionError, NotImplementedError)):
         G.lower_onnx(fp)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# operator spellings a tf2onnx export of the real model may use (floodsr/models/ResUNet_16x_DEM.py:12-24 only describes
+# the network in prose): every variant is lowered and executed against the oracle's interpreter of the same file
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("variant", ["pad_valid", "stride2", "stride2_tf", "bilinear_half_pixel", "bilinear_align_corners",
+                                     "bilinear_asymmetric", "unfolded_bn", "clip_sigmoid", "reshape_cast", "everything"])
+def test_export_spelling_variants_lower_and_match_the_oracle(tmp_path, variant):
+    from tests import h1_variants as V
+
+    m = build_h1_model(seed=6)
+    n_elt = 0
+    if variant == "pad_valid":
+        V.explicit_pad_before_valid_conv(m)
+    elif variant == "stride2":
+        V.strided_conv_downsampling(m, level=1)
+    elif variant == "stride2_tf":
+        V.strided_conv_downsampling(m, level=0, tf_style=True)
+    elif variant.startswith("bilinear_"):
+        V.bilinear_resize(m, variant[len("bilinear_"):], which=(0, 3))
+    elif variant == "unfolded_bn":
+        V.unfolded_batchnorm(m)
+    elif variant == "clip_sigmoid":
+        V.clip_and_sigmoid_activations(m)
+        n_elt = 2  # Clip(0, 1.5) and Sigmoid are element-wise ops; Clip(0, +inf) folds into its convolution as Relu
+    elif variant == "reshape_cast":
+        V.noop_reshape_and_cast(m)
+    else:
+        m = V.everything()
+        n_elt = 2
+    fp = tmp_path / f"{variant}.onnx"
+    save_onnx(m, fp)
+    lm = _check_against_oracle(fp, tol=1e-5)
+    kinds = [op.kind for op in lm.ops]
+    assert kinds[-1] == G.OP_HEAD and kinds.count(G.OP_ELTWISE) == n_elt
+    if variant.startswith("stride2") or variant == "everything":
+        picks = [op for op in lm.ops if op.kind == G.OP_POOL and op.mode == G.POOL_PICK]
+        assert picks and all(op.k == 2 and op.aux in (0, 1) for op in picks)
+        # the activation after a strided convolution folds into the convolution in front of the pick
+        assert all(lm.ops[lm.ops.index(op) - 1].act == G.ACT_RELU for op in picks)
+    if variant == "unfolded_bn":
+        assert kinds.count(G.OP_CONV) == 27  # Mul / Sub / Div folded into the weights and bias
+
+
+def test_lowering_rejects_what_it_cannot_express(tmp_path):
+    from tests import h1_variants as V
+
+    m = build_h1_model(seed=6)
+    conv = [n for n in m.nodes if n.op_type == "Conv"][3]
+    conv.attrs["pads"] = [0, 0, 0, 0]  # a VALID 3x3 convolution shrinks the map: not this network family
+    fp = tmp_path / "valid.onnx"
+    save_onnx(m, fp)
+    with pytest.raises(NotImplementedError, match="not a 'same' convolution"):
+        G.lower_onnx(fp)
+    m = V.bilinear_resize(build_h1_model(seed=6), "tf_crop_and_resize", which=(1,))
+    fp = tmp_path / "crop.onnx"
+    save_onnx(m, fp)
+    with pytest.raises(NotImplementedError, match="coordinate_transformation_mode"):
+        G.lower_onnx(fp)

@@ -22,6 +22,15 @@ def test_geotiff_round_trip(tmp_path, compression):
     assert tuple(r["geo_tags"][TAG_GEOKEYS]) == UTM32
 
 
+@pytest.mark.parametrize("nodata", [float("nan"), float("inf"), float("-inf"), -3.4028234663852886e38, 0.5])
+def test_non_integer_and_non_finite_nodata_round_trips(tmp_path, nodata):
+    """GDAL_NODATA "nan" is what float DEMs usually carry: writing the prediction next to such a DEM must not fail."""
+    arr = np.ones((8, 8), np.float32)
+    fp = write_geotiff(tmp_path / "n.tif", arr, (1.0, 0.0, 0.0, 0.0, -1.0, 8.0), nodata=nodata, geo_tags={TAG_GEOKEYS: UTM32})
+    got = read_geotiff(fp)["nodata"]
+    assert (np.isnan(got) and np.isnan(nodata)) or got == nodata
+
+
 def test_pixel_is_point_shift_round_trips(tmp_path):
     arr = np.zeros((10, 20), np.float32)
     t = (2.0, 0.0, 100.0, 0.0, -2.0, 900.0)
