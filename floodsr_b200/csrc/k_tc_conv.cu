@@ -94,7 +94,7 @@ struct ConvTcParams {
   __nv_bfloat16* out;          // CP8 output
 };
 
-template <int BN, int PAIR>
+template <int BN, int PAIR, int PARTS>
 __global__ void __launch_bounds__(kConvThreads<PAIR>, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -103,8 +103,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // their TMA latencies overlap.  With PAIR == 2 a CTA computes TWO M tiles (adjacent image blocks at the same
   // output position, so the same taps and weights): every weight slice fetched from L2 feeds two MMAs, one per
   // accumulator, each issued by its own warp.
-  const int kABytesMax = p.parts * p.kc * 128 * 16;
-  const int kBBytesMax = p.parts * p.kc * BN * 16;
+  const int kABytesMax = PARTS * p.kc * 128 * 16;
+  const int kBBytesMax = PARTS * p.kc * BN * 16;
   const int a_stage = PAIR * kABytesMax;
   uint8_t* smem_a = smem_raw;                                   // p.stages x pair x a_bytes
   uint8_t* smem_b = smem_raw + p.stages * a_stage;                // p.stages x b_bytes
@@ -151,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, (uint32_t)(PAIR * BN * (p.parts == 2 ? p.nacc + 1 : 1)));
+    tmem_alloc(tmem_slot, (uint32_t)(PAIR * BN * (PARTS == 2 ? p.nacc + 1 : 1)));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -181,7 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (p.im) tma_load_5d(dst, tm, &full[s], (tn0 + h) * 256, (ty + dy) * p.W + tx + dx, chunk0, 0, 0);
             else tma_load_5d(dst, tm, &full[s], 2 * (tx * p.bw + dx), ty * p.bh + dy, (tn0 + h) * p.bn, chunk0, 0);
           }
-          const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)p.parts * p.kc * BN * 8);
+          const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)PARTS * p.kc * BN * 8);
           bulk_load_1d(smem_b + s * kBBytesMax, wsrc, b_bytes, &full[s]);
         }
       }
@@ -205,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         if (leader) {
           // one MMA consumes two 8-channel planes: LBO = plane stride, SBO = 8 rows x 16 B
-          if (p.parts == 2) {
+          if (PARTS == 2) {
             // stage `it` adds its hi*hi products to accumulator it % nacc; + a_lo * b_hi + a_hi * b_lo go to accumulator nacc
             const uint32_t dm = d + (uint32_t)(it % p.nacc) * BN, ds = d + (uint32_t)p.nacc * BN;
             for (int j = 0; j < kpairs; ++j) {
@@ -242,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                  : ((long long)n_img * p.H + (ty * p.bh + ly)) * p.W + (tx * p.bw + lx);
       // the first tile's residual is fetched while the MMAs still run
       uint4 resv[BN / 8];
-      if (p.res && valid && p.parts == 1) {
+      if (p.res && valid && PARTS == 1) {
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c) {
           const int co = n_tile * BN + c * 8;
@@ -254,26 +254,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN;
-      const int n_extra = p.parts == 2 ? (n_iters_cta < p.nacc ? n_iters_cta : p.nacc) : 0;  // accumulators beyond the first
+      const int n_extra = PARTS == 2 ? (n_iters_cta < p.nacc ? n_iters_cta : p.nacc) : 0;  // accumulators beyond the first
 #pragma unroll
       for (int c = 0; c < BN / 8; ++c) {
         float v[8];
         tmem_ld8(taddr + c * 8, v);
-        tmem_ld_wait();
-        if (p.parts == 2) {
-          // fixed summation order: main accumulators 1 .. used - 1, then the small-product accumulator (index nacc)
-          for (int a = 1; a <= n_extra; ++a) {
-            float u[8];
-            tmem_ld8(taddr + (uint32_t)(a == n_extra ? p.nacc : a) * BN + c * 8, u);
-            tmem_ld_wait();
+        if (PARTS == 2) {
+          // all partial accumulators of this column chunk in flight at once, ONE wait; fixed summation order: main
+          // accumulators 1 .. used - 1, then the small-product accumulator (index nacc)
+          float u[7][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += u[i];
-          }
+          for (int a = 1; a <= 7; ++a)
+            if (a <= n_extra) tmem_ld8(taddr + (uint32_t)(a == n_extra ? p.nacc : a) * BN + c * 8, u[a - 1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int a = 1; a <= 7; ++a)
+            if (a <= n_extra) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += u[a - 1][i];
+            }
+        } else {
+          tmem_ld_wait();
         }
         const int co = n_tile * BN + c * 8;
         if (valid && co < p.cout) {
           const long long off = ((long long)(co >> 3) * p.plane + pix) * 8;
-          if (p.parts == 2) {
+          if (PARTS == 2) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
           }
@@ -285,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if (p.res) {
             float r[8];
-            if (p.parts == 2)
+            if (PARTS == 2)
               join_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), __ldg(reinterpret_cast<const uint4*>(p.res + p.lo_off + off)), r);
             else
               unpack_x8(resv[c], r, p.half);
@@ -299,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * p.alpha;
           }
-          if (p.parts == 2) {
+          if (PARTS == 2) {
             uint4 hi, lo;
             split_x8(v, hi, lo);
             *reinterpret_cast<uint4*>(p.out + off) = hi;
@@ -315,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)(PAIR * BN * (p.parts == 2 ? p.nacc + 1 : 1)));
+    tmem_dealloc(tmem_base, (uint32_t)(PAIR * BN * (PARTS == 2 ? p.nacc + 1 : 1)));
   }
 }
 
@@ -366,13 +372,13 @@ struct ConvRowsParams {
   __nv_bfloat16* out;
 };
 
-template <int BN>
+template <int BN, int PARTS>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const ConvRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   griddep_launch_dependents();
   const int plane_b = p.box_rows * p.pitch * 16;    // one 8-channel plane of a halo box
-  const int box_bytes = p.parts * p.kc * plane_b;   // [part][kc][box_rows * pitch px][16 B], one TMA box
+  const int box_bytes = PARTS * p.kc * plane_b;   // [part][kc][box_rows * pitch px][16 B], one TMA box
   const int stage_bytes = (box_bytes + 2 * p.pitch * 16 + 127) & ~127;  // slack: the last taps of padding positions read past the box
   const int w_round = (p.w_bytes + 1023) & ~1023;
   uint8_t* smem_w = smem_raw;
@@ -388,8 +394,8 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = p.g0 + p.g1;
-  const int buf_cols = (p.parts == 2 ? p.nacc + 1 : 1) * BN;  // TMEM columns of one accumulator buffer
-  const uint32_t tmem_cols = p.parts == 2 ? (uint32_t)(p.sets * buf_cols) : (uint32_t)kRowsTmemCols<BN>;  // host: a power of two >= 32
+  const int buf_cols = (PARTS == 2 ? p.nacc + 1 : 1) * BN;  // TMEM columns of one accumulator buffer
+  const uint32_t tmem_cols = PARTS == 2 ? (uint32_t)(p.sets * buf_cols) : (uint32_t)kRowsTmemCols<BN>;  // host: a power of two >= 32
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -500,7 +506,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t a_t = a_s + (tap / 3) * row_u + (tap % 3);
             const uint32_t b_t = b_g + tap * wtap_u;
-            if (p.parts == 2) {
+            if (PARTS == 2) {
               // hi*hi products of step q = g * 9 + tap go to accumulator q % nacc (nacc <= 9: every accumulator is written in
               // the first group); + a_lo * w_hi + a_hi * w_lo to accumulator nacc
               const int q = g * 9 + tap;
@@ -557,7 +563,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const bool valid = x < p.W && y < p.H;   // padding positions are dropped
       const long long pix = ((long long)img * p.H + y) * p.W + x;
       uint4 resv[BN / 8];  // fetched while the tile's MMAs still run
-      if (p.res && valid && p.parts == 1) {
+      if (p.res && valid && PARTS == 1) {
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c) resv[c] = __ldg(reinterpret_cast<const uint4*>(p.res + ((long long)c * p.plane + pix) * 8));
       }
@@ -571,7 +577,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         float v[32];
         tmem_ld32(taddr + c32 * 32, v);
         tmem_ld_wait();
-        if (p.parts == 2) {
+        if (PARTS == 2) {
           // sum of the partial accumulators in a fixed order: main 1 .. nacc - 1, then the small-product accumulator
           for (int a = 1; a <= p.nacc; ++a) {
             float u[32];
@@ -602,7 +608,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             }
             if (p.res) {
               float r[8];
-              if (p.parts == 2)
+              if (PARTS == 2)
                 join_x8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), __ldg(reinterpret_cast<const uint4*>(p.res + p.lo_off + off)), r);
               else
                 unpack_x8(resv[c32 * 4 + c], r, p.half);
@@ -616,7 +622,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.0f ? o[i] : o[i] * p.alpha;
             }
-            if (p.parts == 2) {
+            if (PARTS == 2) {
               uint4 hi, lo;
               split_x8(o, hi, lo);
               *reinterpret_cast<uint4*>(p.out + off) = hi;
@@ -1048,33 +1054,37 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   if (BN == 128) {
     static bool attr = false;
     if (!attr) {
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
     p.stages = conv_stages<128>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc * parts, p.stages, 2), s, m0, m1, p);
-    else launch_pdl(conv_tc_kernel<128, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
+    if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<128, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else if (BN == 64) {
     static bool attr = false;
     if (!attr) {
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
     p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && 64 * (p.nacc + 1) > 256);
-    if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
-    else launch_pdl(conv_tc_kernel<64, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
+    if (parts == 2) launch_pdl(conv_tc_kernel<64, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
+    else if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<64, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else {
     static bool attr = false;
     if (!attr) {
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
     p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && 32 * (p.nacc + 1) > 256);
-    if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
-    else launch_pdl(conv_tc_kernel<32, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
+    if (parts == 2) launch_pdl(conv_tc_kernel<32, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
+    else if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else launch_pdl(conv_tc_kernel<32, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
   }
   FSR_LAUNCH_CHECK();
 }
@@ -1136,12 +1146,16 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   p.stages = (int)std::min<size_t>(kRowMaxStages, (200 * 1024 - 512 - w_round) / stage_bytes);
   const size_t smem = w_round + (size_t)p.stages * stage_bytes + 512;  // barriers (256 B) + bias (256 B)
   const int grid = p.n_mtiles < n_sms ? p.n_mtiles : n_sms;
+  auto go = [&](auto kernel) {
+    FSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    launch_pdl(kernel, dim3((unsigned)grid), kRowsThreads, smem, s, m0, m1, p);
+  };
   if (cout == 64) {
-    FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    launch_pdl(conv_rows_tc_kernel<64>, dim3((unsigned)grid), kRowsThreads, smem, s, m0, m1, p);
+    if (parts == 2) go(conv_rows_tc_kernel<64, 2>);
+    else go(conv_rows_tc_kernel<64, 1>);
   } else {
-    FSR_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    launch_pdl(conv_rows_tc_kernel<32>, dim3((unsigned)grid), kRowsThreads, smem, s, m0, m1, p);
+    if (parts == 2) go(conv_rows_tc_kernel<32, 2>);
+    else go(conv_rows_tc_kernel<32, 1>);
   }
   FSR_LAUNCH_CHECK();
   if (d_stats) {
