@@ -37,6 +37,7 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_REQUIRE(precision != 1, "precision mode 1 (bf16 operands) was retired: it misses the 1e-2 m bound; use FSR_PREC_FP16");
   FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_FP16 || precision == FSR_PREC_FP32_SIMT, "unknown precision mode");
   if (const char* e = getenv("FSR_BAND_TILES")) band_tiles_ = std::max(1, atoi(e));
+  no_lazy_dem_ = getenv("FSR_NO_LAZY_DEM") != nullptr;
 
   const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
   big_.assign(tensors_.size(), 0);
@@ -130,6 +131,16 @@ Engine::~Engine() {
   if (s_comp) cudaStreamDestroy(s_comp);
   if (s_in) cudaStreamDestroy(s_in);
   if (s_out) cudaStreamDestroy(s_out);
+}
+
+bool Engine::lazy_dem_ok() const {
+  if (precision_ == FSR_PREC_FP32_SIMT || fused_ct_ < 0 || pooled_op_ < 0) return false;
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    if ((int)i == pooled_op_ || (int)i == fused_hd_) continue;
+    const fsr_op& op = ops_[i];
+    if (op.src0 == 1 || op.src1 == 1 || op.res == 1) return false;
+  }
+  return ops_[fused_hd_].src1 == 1 && ops_[pooled_op_].src0 == 1;
 }
 
 int64_t Engine::macs_per_tile() const {
@@ -242,7 +253,7 @@ void Engine::forward(int n_tiles, const float* d_depth_norm, const float* d_dem_
     ensure_arena(n);
     for (size_t i = 0; i < tensors_.size(); ++i) tbase_[i] = tbuf_[i].as<float>();
     tbase_[0] = const_cast<float*>(d_depth_norm) + (size_t)c0 * lr_px;
-    tbase_[1] = const_cast<float*>(d_dem_norm) + (size_t)c0 * hr_px;
+    tbase_[1] = d_dem_norm ? const_cast<float*>(d_dem_norm) + (size_t)c0 * hr_px : nullptr;
     skip_op_ = -1;
     if (dem_lr_pre_ && pooled_op_ >= 0) {
       tbase_[ops_[pooled_op_].dst] = const_cast<float*>(dem_lr_pre_) + (size_t)c0 * lr_px;
@@ -275,15 +286,33 @@ void Engine::run_tiles_from_grid(const float* d_depth, const float* d_dem, const
   for (int c0 = 0; c0 < n_tiles; c0 += chunk_tiles_) {
     const int n = std::min(chunk_tiles_, n_tiles - c0);
     ensure_arena(n);
+    // The normalised DEM tile is not materialised when its only readers are the pooled low-resolution branch (produced by
+    // the normalisation kernel itself) and the fused high-resolution kernel (which then normalises the raster window from
+    // the tile's statistics): one 1 MiB write and one 1 MiB read per tile less.  FSR_NO_LAZY_DEM=1 keeps the old path (A/B).
+    const bool lazy = p.normalize_inputs && !no_lazy_dem_ && lazy_dem_ok();
     {
       ProfScope scope(prof, PROF_PROLOGUE, s);
-      launch_tile_normalize(d_dem, d_depth, grid, tile_base + c0, n, T, TL, hdr_.scale, p, d_dem_norm_.as<float>(),
+      launch_tile_normalize(d_dem, d_depth, grid, tile_base + c0, n, T, TL, hdr_.scale, p, lazy ? nullptr : d_dem_norm_.as<float>(),
                             d_depth_norm_.as<float>(), d_stats_out, d_dem_lr_.as<float>(), d_flags(), s);
     }
     dem_lr_pre_ = p.normalize_inputs ? d_dem_lr_.as<float>() : nullptr;
+    dem_src_ = DemSource{};
+    if (lazy) {
+      dem_src_.on = 1;
+      dem_src_.ras = d_dem;
+      dem_src_.origins = grid.origins + tile_base + c0;
+      dem_src_.stats = d_stats_out + (size_t)(tile_base + c0) * 3;
+      dem_src_.H = grid.H;
+      dem_src_.W = grid.W;
+      dem_src_.has_nodata = p.has_dem_nodata;
+      dem_src_.nodata = p.dem_nodata;
+      dem_src_.nodata_tol = p.dem_nodata_tol;
+    }
     float* pn = d_pred_norm ? d_pred_norm + (size_t)c0 * hr_px : nullptr;
-    forward(n, d_depth_norm_.as<float>(), d_dem_norm_.as<float>(), pn, d_pred_m + (size_t)c0 * hr_px, p.max_depth, p.depth_denom, s);
+    forward(n, d_depth_norm_.as<float>(), lazy ? nullptr : d_dem_norm_.as<float>(), pn, d_pred_m + (size_t)c0 * hr_px, p.max_depth,
+            p.depth_denom, s);
     dem_lr_pre_ = nullptr;
+    dem_src_ = DemSource{};
   }
 }
 

@@ -28,6 +28,38 @@ struct BlendGeom {
 };
 
 
+// Where the fused high-resolution kernels take the normalised DEM from.  on == 0: `tiles` holds the normalised tiles
+// [n][T][T] (stage calls, pre-normalised inputs).  on == 1: the kernel reads every tile's window straight out of the raw
+// raster and applies normalize_dem_with_stats_np (floodsr/preprocessing.py:61-94) itself from the tile's statistics, with
+// the operation sequence of the normalisation kernel (k_prologue.cu, pass N): the normalised tile never exists in HBM.
+struct DemSource {
+  int on = 0;
+  const float* ras = nullptr;     // raw raster rows (row 0 = first row the launch's windows may read)
+  const int2* origins = nullptr;  // [n] window origins (y0, x0) relative to `ras`
+  const float* stats = nullptr;   // [n][3] p_clip, dem_min, dem_max
+  int H = 0, W = 0;               // valid raster extent (pixels beyond it read as 0)
+  int has_nodata = 0;
+  float nodata = 0.f, nodata_tol = -1.f;
+};
+
+// one pixel of normalize_dem_with_stats_np; (p_clip, dem_min, range, zero_out) from dem_norm_spec()
+__device__ __forceinline__ float dem_normalise_px(float x, const DemSource& d, float p_clip, float dem_min, float range_f, bool zero_out) {
+  if (d.has_nodata) {
+    const bool hit = (x == d.nodata) || (d.nodata_tol >= 0.0f && fabsf(x - d.nodata) <= d.nodata_tol);
+    if (hit) x = 0.0f;
+  }
+  x = fminf(fmaxf(x, 0.0f), p_clip);
+  const float n = __fdiv_rn(__fsub_rn(x, dem_min), range_f);
+  return zero_out ? 0.0f : fminf(fmaxf(n, 0.0f), 1.0f);
+}
+__device__ __forceinline__ void dem_norm_spec(const float* stats3, float& p_clip, float& dem_min, float& range_f, bool& zero_out) {
+  p_clip = stats3[0];
+  dem_min = stats3[1];
+  const double range_d = (double)stats3[2] - (double)dem_min;  // python-float subtraction in the reference
+  zero_out = !(range_d > 0.0);
+  range_f = (float)range_d;
+}
+
 struct DeviceBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -209,6 +241,9 @@ class Engine {
   std::vector<float*> tbase_;    // per-forward tensor base pointers (inputs/outputs alias caller buffers)
   DeviceBuf d_dem_norm_, d_depth_norm_, d_pred_norm_, d_dem_lr_;
   const float* dem_lr_pre_ = nullptr;  // pooled normalised DEM written by the normalisation kernel for the current batch
+  bool no_lazy_dem_ = false;           // FSR_NO_LAZY_DEM at construction: always materialise the normalised DEM tiles
+  DemSource dem_src_;                  // current batch: the fused kernel normalises the raw raster windows itself (on == 1)
+  bool lazy_dem_ok() const;            // the plan reads dem_hr only through the pooled branch and the fused head
   int skip_op_ = -1;                   // op skipped by the current forward pass
   int pooled_op_ = -1;                 // plan op it replaces (scale x scale average pool of the DEM input), or -1
 };

@@ -428,7 +428,9 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
   // ---- pass N: clip to [0, p_clip], min-max scale, clip to [0, 1] (preprocessing.py:91-94) -----------
   // plus, when dem_lr != nullptr, the scale x scale average pooling of the normalised tile that feeds the network's
   // low-resolution branch (the graph's AveragePool on dem_hr): fixed summation order, no atomics.
-  float4* out = reinterpret_cast<float4*>(dem_norm + (size_t)tile_local * T * T);
+  // dem_norm == nullptr: the consumer (the fused high-resolution kernel) normalises the raster window itself from `stats`
+  // with this very sequence of operations, so the 1 MiB per tile is neither written here nor read back there
+  float4* out = dem_norm ? reinterpret_cast<float4*>(dem_norm + (size_t)tile_local * T * T) : nullptr;
   const bool pool = dem_lr != nullptr && scale == 16 && T == 512 && kUnroll % 4 == 0;  // thread <-> (row offset t / 128, column vector t % 128)
   for (int i0 = t; i0 < n_vec; i0 += kThreads * kUnroll) {
     float4 vv[kUnroll];
@@ -449,7 +451,7 @@ tile_normalize_kernel(const float* __restrict__ dem, const float* __restrict__ d
         float n = __fdiv_rn(__fsub_rn(x, dem_min), range_f);
         e[j] = zero_out ? 0.0f : fminf(fmaxf(n, 0.0f), 1.0f);
       }
-      out[i0 + u * kThreads] = make_float4(e[0], e[1], e[2], e[3]);
+      if (out) out[i0 + u * kThreads] = make_float4(e[0], e[1], e[2], e[3]);
       psum[u / 4] += (e[0] + e[1]) + (e[2] + e[3]);
     }
     if (pool) {

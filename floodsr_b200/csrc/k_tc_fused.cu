@@ -72,7 +72,8 @@ struct FusedParams {
   float max_depth, denom;
   const __nv_bfloat16* hw;      // head weights, kHwBytes
   const __nv_bfloat16* wt;      // convT weights [16 ky][kWtRow]
-  const float* dem;     // [N][H][512] normalised DEM
+  const float* dem;     // [N][H][512] normalised DEM (src.on == 0)
+  DemSource src;        // or: the raw raster + per-tile statistics (src.on == 1)
   float* pred_m;        // [N][H][512]
   float* pred_norm;     // or nullptr
   float bias_t[kC];     // convT bias
@@ -335,18 +336,28 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
     }
   } else if (warp == 2) {
     // ===================== DEM prefetcher: fp32 halo row (514 px) -> smem ===================================
+    // src.on: the row comes from the raw raster window of the tile (zero beyond the raster, as the reference's padding to
+    // whole tiles); the operand builder normalises it.  Pixels outside the TILE are the head convolution's zero padding.
     int fs = 0;
     uint32_t fph = 1;
     for (RowIter it(p); it.next();) {
+      int oy = 0, ox = 0;
+      if (p.src.on) {
+        const int2 org = __ldg(p.src.origins + it.img);
+        oy = org.x;
+        ox = org.y;
+      }
       for (int i = 0; i < it.rows + 2; ++i) {
         const int y = it.y0 - 1 + i;
-        const bool yok = y >= 0 && y < p.H;
-        const float* row = p.dem + ((size_t)it.img * p.H + (yok ? y : 0)) * kW;
+        const bool yok = y >= 0 && y < p.H && (!p.src.on || oy + y < p.src.H);
+        const float* row = p.src.on ? p.src.ras + (size_t)(oy + (yok ? y : 0)) * p.src.W + ox
+                                    : p.dem + ((size_t)it.img * p.H + (yok ? y : 0)) * kW;
+        const int x_end = p.src.on ? (p.src.W - ox < kW ? p.src.W - ox : kW) : kW;
         const uint32_t dst = smem_u32(smem_dem + fs * kDemRow);
         wait_relaxed(&f_empty[fs], fph);
         for (int k = lane; k < kRowPx; k += 32) {
           const int x = k - 1;
-          const bool ok = yok && x >= 0 && x < kW;
+          const bool ok = yok && x >= 0 && x < x_end;
           const float* src = row + (ok ? x : 0);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + k * 4), "l"(src), "r"(ok ? 4 : 0) : "memory");
         }
@@ -360,8 +371,22 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
     int fs = 0;
     uint32_t ph = 0;
     for (RowIter it(p); it.next();) {
+      float p_clip = 0.f, dem_min = 0.f, range_f = 1.f;
+      bool zero_out = false;
+      if (p.src.on) dem_norm_spec(p.src.stats + (size_t)it.img * 3, p_clip, dem_min, range_f, zero_out);
       for (int i = 0; i < it.rows + 2; ++i) {
         wait_relaxed(&dem_full[fs], ph);
+        if (p.src.on) {
+          // raw raster values -> normalised DEM, in place; pixels outside the tile stay the convolution's zero padding
+          const int y = it.y0 - 1 + i;
+          const bool in_tile_row = y >= 0 && y < p.H;
+          float* drow = reinterpret_cast<float*>(smem_dem + fs * kDemRow);
+          for (int k = lane; k < kRowPx; k += 32) {
+            const bool in_tile = in_tile_row && k >= 1 && k <= kW;
+            drow[k] = in_tile ? dem_normalise_px(drow[k], p.src, p_clip, dem_min, range_f, zero_out) : 0.0f;
+          }
+          __syncwarp();
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int px0 = g * 128 + lane * 4;
@@ -562,8 +587,8 @@ void fused_pack_convt(const float* w, uint16_t* dst, uint16_t (*cvt)(float)) {
 
 void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfloat16* wt_pack, const float* bias_t, int act_t,
                         float alpha_t, const __nv_bfloat16* hw_pack, const float* w2, const float* b2, int act_h, float alpha_h,
-                        const float* dem, float* pred_m, float* pred_norm, int n_img, int H, float max_depth, float denom,
-                        int half, int n_sms, cudaStream_t s) {
+                        const float* dem, const DemSource& src, float* pred_m, float* pred_norm, int n_img, int H, float max_depth,
+                        float denom, int half, int n_sms, cudaStream_t s) {
   FusedParams p{};
   p.H = H;
   p.N = n_img;
@@ -577,6 +602,7 @@ void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_
   p.hw = hw_pack;
   p.wt = wt_pack;
   p.dem = dem;
+  p.src = src;
   p.pred_m = pred_m;
   p.pred_norm = pred_norm;
   for (int c = 0; c < kC; ++c) {

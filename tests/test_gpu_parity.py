@@ -312,6 +312,36 @@ def test_run_raster_properties_at_mersch_size(engine):
     assert np.array_equal(out1[:384, :384], hard[:384, :384])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_in_kernel_dem_normalisation_is_bit_identical_to_the_materialised_tiles(h1_model_fp, monkeypatch, precision):
+    """By default the fused high-resolution kernel normalises each tile's raster window itself (no dem_norm tensor in HBM);
+    FSR_NO_LAZY_DEM=1 keeps the normalisation kernel's materialised tiles.  Same operation sequence -> same bits: ragged
+    raster (zero padding beyond the raster), nodata replacement, caller-supplied statistics with a negative minimum."""
+    from floodsr_b200.engine import EngineB200
+
+    h, w = 976, 1104
+    depth, dem = synth_raster(h, w, seed=5)
+    lazy = EngineB200(h1_model_fp, precision=precision)
+    monkeypatch.setenv("FSR_NO_LAZY_DEM", "1")
+    mat = EngineB200(h1_model_fp, precision=precision)
+    monkeypatch.delenv("FSR_NO_LAZY_DEM")
+    for method in ("feather", "hard"):
+        a, na, sa = lazy.run_raster(depth, dem, window_method=method)
+        b, nb, sb = mat.run_raster(depth, dem, window_method=method)
+        assert na == nb and sa == sb and np.array_equal(a, b), method
+    d_t = np.stack([synth_depth(32, 32, seed=70 + i) for i in range(3)])
+    e_t = np.stack([synth_dem(512, 512, seed=70 + i) for i in range(3)])
+    e_t[1, 100:140, 200:260] = -9999.0
+    ref = {"p_clip": 900.0, "dem_min": -50.0, "dem_max": 900.0}
+    for kw in ({}, {"dem_ref_stats": ref}, {"dem_pct_clip": 37.5}, {"dem_hr_nodata": -9999.0}):
+        a = lazy.run_tiles(d_t, e_t, **kw)
+        b = mat.run_tiles(d_t, e_t, **kw)
+        assert np.array_equal(a["prediction_m"], b["prediction_m"]) and np.array_equal(a["prediction_norm"], b["prediction_norm"]), kw
+        assert a["dem_stats_used"] == b["dem_stats_used"]
+    lazy.close()
+    mat.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # graphs other than H1: operator spellings of a tf2onnx export, other widths (the loader runs whatever the file holds)
 # ---------------------------------------------------------------------------------------------------------
