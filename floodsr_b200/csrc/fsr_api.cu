@@ -496,6 +496,37 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
   }
 }
 
+// Sub-bands of the window rows [ty0, ty1) for the copy / compute pipelines: enough windows per band to keep the batched layer
+// kernels efficient, small enough to overlap copies; the first band is a single window row so that the pipeline fills fast.
+// A band must own at least the rows it receives partial sums for (three or more window rows covering one coordinate:
+// overlap >= tile / 2 or a forced trailing window close to its predecessor): such a band takes over the following window rows.
+static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1) {
+  const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T, H = e.win.H;
+  const int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
+  std::vector<int> band_ty{ty0};  // band b covers window rows [band_ty[b], band_ty[b + 1])
+  if (ty1 - ty0 >= 3 && rows_per_band > 1) band_ty.push_back(ty0 + 1);
+  while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
+  band_ty.push_back(ty1);
+  for (size_t b = 0; b + 1 < band_ty.size();) {
+    const bool receives = band_ty[b] > 0;
+    const int halo_end = receives ? std::min(e.win.ys[band_ty[b] - 1] + T, H) : 0;
+    if (receives && band_ty[b + 1] < ty1 && band_ty[b + 1] < ny && std::min(e.win.ys[band_ty[b + 1]], H) < halo_end)
+      band_ty.erase(band_ty.begin() + b + 1);
+    else
+      ++b;
+  }
+  // the last sub-band cannot grow downwards: if it is still too short, it joins the one above it
+  while (band_ty.size() > 2) {
+    const int start = band_ty[band_ty.size() - 2];
+    const int row_end = ty1 >= ny ? H : std::min(e.win.ys[ty1], H);
+    if (start > 0 && row_end - std::min(e.win.ys[start], H) < std::min(e.win.ys[start - 1] + T, H) - std::min(e.win.ys[start], H))
+      band_ty.erase(band_ty.end() - 2);
+    else
+      break;
+  }
+  return band_ty;
+}
+
 static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s,
                           const DeviceBuf* tiles_buf = nullptr, const BandState* st = nullptr, int row_begin = 0, int row_end = -1) {
   BlendGeom g = e.blend_geom();
@@ -660,22 +691,9 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   e.d_in_dem.ensure((size_t)H * W * sizeof(float));
   e.d_out.ensure((size_t)H * W * sizeof(float));
   e.d_stats.ensure((size_t)ny * nx * 3 * sizeof(float));
-  // band plan: enough windows per band to keep the batched layer kernels efficient, small enough to overlap copies;
-  // the first band is a single window row, so the pipeline fills fast (first H2D); a single-row LAST band was measured
-  // slower than letting the last band keep its two rows (small batches run the LR layers at a third of their throughput)
-  int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
-  std::vector<int> band_ty;  // band b covers window rows [band_ty[b], band_ty[b + 1])
-  band_ty.push_back(0);
-  if (ny >= 3 && rows_per_band > 1) band_ty.push_back(1);
-  while (band_ty.back() + rows_per_band < ny) band_ty.push_back(band_ty.back() + rows_per_band);
-  band_ty.push_back(ny);
-  // a band must own at least the rows it receives partial sums for (three or more window rows covering one coordinate:
-  // overlap >= tile / 2 or a forced trailing window): such a band takes over the following window rows
-  for (size_t b = 1; b + 1 < band_ty.size();) {
-    const int halo_end = std::min(e.win.ys[band_ty[b] - 1] + T, (int)H);
-    if (band_ty[b + 1] < ny && std::min(e.win.ys[band_ty[b + 1]], (int)H) < halo_end) band_ty.erase(band_ty.begin() + b + 1);
-    else ++b;
-  }
+  // (a single-row LAST band was measured slower than letting the last band keep its two rows: small batches run the LR
+  // layers at a third of their throughput)
+  const std::vector<int> band_ty = sub_band_plan(e, 0, ny);
   const int n_bands = (int)band_ty.size() - 1;
   e.d_halo[0].ensure((size_t)T * W * sizeof(float));
   e.d_halo[1].ensure((size_t)T * W * sizeof(float));
@@ -857,13 +875,7 @@ int fsr_band_host_begin(fsr_engine* eng, const float* depth_lr, const float* dem
     FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, sc_));
     FSR_CUDA(cudaStreamSynchronize(sc_));
   }
-  // sub-band plan: a single window row first, like fsr_run_raster
-  const int n_rows_rank = ty1 - ty0;
-  int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
-  std::vector<int> band_ty{ty0};
-  if (n_rows_rank >= 3 && rows_per_band > 1) band_ty.push_back(ty0 + 1);
-  while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
-  band_ty.push_back(ty1);
+  const std::vector<int> band_ty = sub_band_plan(e, ty0, ty1);
   const int n_bands = (int)band_ty.size() - 1;
   std::vector<cudaEvent_t> ev_in(n_bands), ev_done(n_bands);
   for (int b = 0; b < n_bands; ++b) {

@@ -463,6 +463,28 @@ def test_config4_8k_raster_vs_oracle(engine, oracle_engine, h1_model_fp):
     assert _wet_mask_agrees(got16, want, 1e-2)
 
 
+@pytest.mark.parametrize("h,w,ov", [(1536, 1024, 12), (2048, 528, 20), (1600, 640, 17)])
+def test_large_overlaps_three_window_rows_per_coordinate(h1_model_fp, oracle_engine, monkeypatch, h, w, ov):
+    """overlap_lr >= 17 (or 12 with a forced trailing window at H = 1536: window rows [0, 320, 640, 960, 1024]) covers
+    coordinates with three or more window rows.  With one window row per pipeline band (FSR_BAND_TILES=1) a band would own
+    fewer rows than its incoming halo covers unless the planner merges window rows: the mosaic must still equal the oracle's."""
+    from floodsr_b200.engine import EngineB200
+    from oracle.stitch_np import run_tiled
+
+    monkeypatch.setenv("FSR_BAND_TILES", "1")
+    eng = EngineB200(h1_model_fp, precision="fp16")
+    monkeypatch.delenv("FSR_BAND_TILES")
+    depth, dem = synth_raster(h, w, seed=h + w)
+    tiles_engine = EngineB200(h1_model_fp, precision="fp16")  # default band size: the reference for bit identity
+    want_bits, n_ref, _ = tiles_engine.run_raster(depth, dem, overlap_lr=ov)
+    got, n, _ = eng.run_raster(depth, dem, overlap_lr=ov)
+    assert n == n_ref and np.array_equal(got, want_bits)
+    want, n_tiles, _ = run_tiled(oracle_engine, depth, dem, window_method="feather", overlap_lr=ov)
+    assert n == n_tiles and np.abs(got - want).max() <= 1e-2
+    eng.close()
+    tiles_engine.close()
+
+
 def test_run_raster_input_assertions(engine):
     depth, dem = synth_raster(1024, 1024, seed=3)
     with pytest.raises(AssertionError, match="depth shape"):
