@@ -80,9 +80,11 @@ def find_model(tmpdir: Path) -> tuple[Path, str]:
     return write_h1_model(tmpdir / ver / "model_infer.onnx", seed=0), "random-init H1 graph (12,045,568 parameters; release asset unavailable offline)"
 
 
-def bind_to_gpu_numa_node(device_index: int) -> None:
+def bind_to_gpu_numa_node(device_index: int):
     """Run this process (its pinned allocations, the copy-engine doorbells, the NCCL proxy) on the CPUs of the GPU's NUMA
-    node.  Best effort: silently skipped when the topology files are not readable (containers without /sys access)."""
+    node.  Best effort: silently skipped when the topology files are not readable (containers without /sys access).
+    Returns the affinity mask to restore for CPU-side work (the cpu_baseline leg uses every allowed core)."""
+    before = os.sched_getaffinity(0)
     try:
         import pynvml
 
@@ -93,7 +95,7 @@ def bind_to_gpu_numa_node(device_index: int) -> None:
         node_fp = Path("/sys/bus/pci/devices") / bus.lower()[-12:] / "numa_node"
         node = int(node_fp.read_text().strip())
         if node < 0:
-            return
+            return before
         cpus = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
         ids: set[int] = set()
         for part in cpus.split(","):
@@ -103,7 +105,8 @@ def bind_to_gpu_numa_node(device_index: int) -> None:
         if ids & allowed:
             os.sched_setaffinity(0, ids & allowed)
     except Exception:
-        return
+        pass
+    return before
 
 
 class ClockSampler:
@@ -166,7 +169,7 @@ def cpu_reference_rate(model_fp: Path, sample_hw=(2048, 3072), steps: int = 1, w
     from oracle.engine_ref import OracleEngine
     from oracle.stitch_np import run_tiled
 
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
     torch.set_num_threads(cores)
     eng = OracleEngine(model_fp, threads=cores)
     h, w = sample_hw
@@ -428,7 +431,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: floodsr_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    bind_to_gpu_numa_node(local_rank)
+    affinity_before = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
@@ -531,6 +534,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, affinity_before)  # the CPU leg runs on every core this process may use
         cb = cpu_reference_rate(model_fp, steps=2, warmup=1)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 

@@ -53,6 +53,10 @@ def kernel(src, dst, tiles, flops_per_tile, index=0):
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "sm__cycles_elapsed.max.per_second",
         "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum", "sm__sass_inst_executed_op_utcmma.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_a.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_b_scope_1cta.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "smsp__cycles_active.avg",
     ]
     rec = OrderedDict()
     for h, u, v in zip(hdr, units, vals):
@@ -65,8 +69,18 @@ def kernel(src, dst, tiles, flops_per_tile, index=0):
     rd = num("dram__bytes_read.sum") * scale[rec["dram__bytes_read.sum"]["unit"]]
     wr = num("dram__bytes_write.sum") * scale[rec["dram__bytes_write.sum"]["unit"]]
     us = num("gpu__time_duration.sum") * {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}[rec["gpu__time_duration.sum"]["unit"]]
+    tensor_pct, tensor_metric = None, None
+    for key in ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"):
+        try:
+            tensor_pct, tensor_metric = num(key), key
+            break
+        except (KeyError, ValueError):
+            continue
     summary = {
         "source": src,
+        "tensor_pipe_pct": tensor_pct,
+        "tensor_pipe_metric": tensor_metric,
         "tiles_in_launch": tiles,
         "flops_per_launch": tiles * flops_per_tile,
         "dram_bytes_read": rd,
