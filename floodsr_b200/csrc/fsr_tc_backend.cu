@@ -16,7 +16,7 @@
 namespace fsr {
 
 // launchers implemented in k_tc_conv.cu / k_tc_head.cu
-int conv_tc_bn(int cout, int parts);
+int conv_tc_bn(int cout, int parts, int hh_steps);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
@@ -198,10 +198,10 @@ void Engine::tc_prepare(const float* w) {
       t.kc = kc;
       t.C0 = C0;
       t.C1 = C1;
-      const int BN = t.rows ? op.cout : conv_tc_bn(op.cout, parts_);
-      const int n_tiles = ceil_div(op.cout, BN);
       const int taps = op.k * op.k;
       const int s0 = (C0 / 8) / kc, s1 = C1 ? (C1 / 8) / kc : 0;
+      const int BN = t.rows ? op.cout : conv_tc_bn(op.cout, parts_, taps * (s0 + s1) * (kc / 2));
+      const int n_tiles = ceil_div(op.cout, BN);
       const int real_c0 = t.pack_small ? tensors_[op.src0].c + (op.src1 >= 0 ? tensors_[op.src1].c : 0) : tensors_[op.src0].c;
       const int real_c1 = t.pack_small ? 0 : (op.src1 >= 0 ? tensors_[op.src1].c : 0);
       const int cin_real = real_c0 + real_c1;

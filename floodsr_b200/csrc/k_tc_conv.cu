@@ -194,7 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t a_lo0 = desc_lo32(smem_u32(smem_a + h * kABytesMax), 128 * 16);
       const uint32_t b_lo0 = desc_lo32(smem_u32(smem_b), BN * 16);
       const uint32_t a_step = (uint32_t)a_stage >> 4, b_step = (uint32_t)kBBytesMax >> 4;
-      const uint32_t d = tmem_base + h * BN;  // split mode runs with PAIR == 1: accumulators [d, d + (nacc + 1) * BN)
+      const uint32_t d = tmem_base + h * BN * (PARTS == 2 ? p.nacc + 1 : 1);  // split mode: accumulators [d, d + (nacc + 1) * BN)
       const int kpairs = p.kc / 2;
       const uint32_t a_part = (uint32_t)(p.kc * 128 * 16) >> 4, b_part = (uint32_t)(p.kc * BN * 16) >> 4;
       const bool leader = elect_one();
@@ -253,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(accum_full, 0);
         tc_fence_after();
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN * (PARTS == 2 ? p.nacc + 1 : 1);
       const int n_extra = PARTS == 2 ? (n_iters_cta < p.nacc ? n_iters_cta : p.nacc) : 0;  // accumulators beyond the first
 #pragma unroll
       for (int c = 0; c < BN / 8; ++c) {
@@ -997,8 +997,26 @@ void conv_tc_tile_box(int H, int W, int& bw, int& bh, int& bn) {
   if (bw * bh * bn != 128 || W % bw || H % bh) throw Error(FSR_E_UNSUPPORTED, "feature-map size does not tile into 128-pixel boxes");
 }
 
-// output channels per CTA; split mode keeps tiles at <= 64 channels so that up to 8 partial accumulators fit in TMEM
-int conv_tc_bn(int cout, int parts) { return (cout >= 128 && parts == 1) ? 128 : (cout >= 64 ? 64 : 32); }
+// Split mode: longest accumulation chain (hi*hi MMAs added into one TMEM accumulator) the configuration may produce.  The
+// tensor core truncates on every addition into an accumulator: measured ~1e-7 relative error per step.  FSR_X3_CHAIN overrides.
+static int split_chain_limit() {
+  static const int v = getenv("FSR_X3_CHAIN") ? std::max(1, atoi(getenv("FSR_X3_CHAIN"))) : 48;
+  return v;
+}
+// accumulators for the hi*hi products (1, 3 or 7: with the one for the small products the allocation is a power of two)
+static int split_nacc(int hh_steps, int max_nacc) {
+  const int lim = split_chain_limit();
+  for (int n : {1, 3, 7})
+    if (n <= max_nacc && (hh_steps + n - 1) / n <= lim) return n;
+  return max_nacc;
+}
+// output channels per CTA.  Split mode (hh_steps = K / 16 > 0): 128-channel tiles leave room for 3 chain accumulators, 64-channel
+// tiles for 7; the wider tile halves the activation traffic per MMA and is taken whenever its chains stay short enough
+int conv_tc_bn(int cout, int parts, int hh_steps) {
+  if (parts == 1) return cout >= 128 ? 128 : (cout >= 64 ? 64 : 32);
+  if (cout >= 128 && (hh_steps + 2) / 3 <= split_chain_limit()) return 128;
+  return cout >= 64 ? 64 : 32;
+}
 
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
@@ -1039,27 +1057,30 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   CUtensorMap m1 = !src1 ? m0
                    : im  ? make_im8_tensor_map(src1, plane1 / ((long long)H * W), H * W, C1 / 8, kc, parts)
                          : make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc, parts);
-  const int BN = conv_tc_bn(cout, parts);
   const int n_iters = ksz * ksz * (p.s0 + p.s1);
   // split mode: 1, 3 or 7 accumulators for the hi*hi products (+ 1 for the small ones; a power-of-two TMEM allocation), so
   // that one accumulation chain stays short: the tensor core truncates on every addition into an accumulator
   const int hh_steps = n_iters * (kc / 2);
-  p.nacc = parts == 2 ? (hh_steps > 48 ? 7 : hh_steps > 12 ? 3 : 1) : 1;
+  const int BN = conv_tc_bn(cout, parts, hh_steps);
+  p.nacc = parts == 2 ? split_nacc(hh_steps, 512 / BN - 1) : 1;
   // Two image blocks per CTA (every weight slice fetched from L2 feeds two MMAs) where it measured faster on B200: maps of
   // <= 16 pixels with enough CTAs left to fill the SMs.  Larger maps have short K loops and many CTAs; there two
   // co-resident single-tile CTAs (8 epilogue warps per SM instead of 4) win.  env FSR_NO_CONV_PAIR disables it.
   const long long n_single = (long long)p.tiles_x * p.tiles_y * tiles_n * ceil_div(cout, BN);
-  p.pair = (parts == 1 && tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR")) ? kConvPairs : 1;
+  p.pair = (tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR") &&
+            (parts == 1 || 2 * BN * (p.nacc + 1) <= 512)) ? kConvPairs : 1;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * ceil_div(tiles_n, p.pair)), (unsigned)ceil_div(cout, BN));
   if (BN == 128) {
     static bool attr = false;
     if (!attr) {
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<128>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair);
-    if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc * parts, p.stages, 2), s, m0, m1, p);
+    p.stages = conv_stages<128>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2);
+    if (parts == 2) launch_pdl(conv_tc_kernel<128, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
+    else if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<128, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else if (BN == 64) {
     static bool attr = false;
@@ -1067,10 +1088,12 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && 64 * (p.nacc + 1) > 256);
-    if (parts == 2) launch_pdl(conv_tc_kernel<64, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
+    p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && p.pair * 64 * (p.nacc + 1) > 256);
+    if (parts == 2 && p.pair == 2) launch_pdl(conv_tc_kernel<64, 2, 2>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else if (parts == 2) launch_pdl(conv_tc_kernel<64, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
     else if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<64, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else {
@@ -1079,10 +1102,12 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
-    p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && 32 * (p.nacc + 1) > 256);
-    if (parts == 2) launch_pdl(conv_tc_kernel<32, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
+    p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && p.pair * 32 * (p.nacc + 1) > 256);
+    if (parts == 2 && p.pair == 2) launch_pdl(conv_tc_kernel<32, 2, 2>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
+    else if (parts == 2) launch_pdl(conv_tc_kernel<32, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
     else if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<32, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
   }
