@@ -36,6 +36,7 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_REQUIRE(hdr_.out_tensor >= 2 && hdr_.out_tensor < hdr_.n_tensors, "bad output tensor");
   FSR_REQUIRE(precision != 1, "precision mode 1 (bf16 operands) was retired: it misses the 1e-2 m bound; use FSR_PREC_FP16");
   FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_FP16 || precision == FSR_PREC_FP32_SIMT, "unknown precision mode");
+  if (precision == FSR_PREC_FP32) band_tiles_ = 255;  // compute-bound mode: larger bands (measured e2e 24.8 -> 23.6 ms at 935 windows)
   if (const char* e = getenv("FSR_BAND_TILES")) band_tiles_ = std::max(1, atoi(e));
   no_lazy_dem_ = getenv("FSR_NO_LAZY_DEM") != nullptr;
 
@@ -134,7 +135,9 @@ Engine::~Engine() {
 }
 
 bool Engine::lazy_dem_ok() const {
-  if (precision_ == FSR_PREC_FP32_SIMT || fused_ct_ < 0 || pooled_op_ < 0) return false;
+  // split mode only: there a row of the fused kernel lasts ~4 us and its DEM warp has time for 514 divisions; in the 16-bit
+  // kernel (1.4 us per row) the in-kernel normalisation became the critical path (measured: 4.6 -> 8.6 ms)
+  if (parts_ != 2 || fused_ct_ < 0 || pooled_op_ < 0) return false;
   for (size_t i = 0; i < ops_.size(); ++i) {
     if ((int)i == pooled_op_ || (int)i == fused_hd_) continue;
     const fsr_op& op = ops_[i];
@@ -502,7 +505,10 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
 // overlap >= tile / 2 or a forced trailing window close to its predecessor): such a band takes over the following window rows.
 static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1) {
   const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T, H = e.win.H;
-  const int rows_per_band = std::max(1, ceil_div(e.band_tiles_target(), nx));
+  // band size: the engine's target, but at least ~4 bands per call so that small rasters still overlap copies and kernels
+  const int total = (ty1 - ty0) * nx;
+  const int target = std::min(e.band_tiles_target(), std::max(64, ceil_div(total, 4)));
+  const int rows_per_band = std::max(1, ceil_div(target, nx));
   std::vector<int> band_ty{ty0};  // band b covers window rows [band_ty[b], band_ty[b + 1])
   if (ty1 - ty0 >= 3 && rows_per_band > 1) band_ty.push_back(ty0 + 1);
   while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);

@@ -63,6 +63,7 @@ struct X3Params {
   long long total_rows; // N * H
   float alpha_t, alpha_h;
   float scale_t_inv, scale_h_inv;  // inverse power-of-two factors of the packed convT / head weights
+  unsigned wait_epi_ns, wait_build_ns, wait_dem_ns;  // suspend-time hints of the epilogue / F builder / DEM + loader roles
   float max_depth, denom;
   const __nv_bfloat16* hw;      // head weights, kHwBytes
   const __nv_bfloat16* wt;      // convT weights [16 ky][4 blocks][2 K halves][2 parts][kWtPart]
@@ -96,7 +97,10 @@ struct RowIter {  // items of this CTA's row range; every warp role iterates the
   }
 };
 
-__device__ __forceinline__ void wait_relaxed(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint.  Every poll is a shared-memory access, and the shared-memory data pipe is what bounds this
+// kernel (tensor-core operand wavefronts 75 % + LSU wavefronts 22 % of peak in the ncu capture, a third of the latter barrier
+// polls): roles that have a whole row time (~4 us here) of slack poll rarely, roles on the critical path poll often.
+__device__ __forceinline__ void wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 96u) {
   uint32_t spins = 0;
   for (;;) {
     uint32_t ok;
@@ -107,7 +111,7 @@ __device__ __forceinline__ void wait_relaxed(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(96u)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
         : "memory");
     if (ok) return;
     if (++spins > (1u << 26)) __trap();
@@ -239,7 +243,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
           const int y = it.y0 - 1 + i;
           if (y < 0 || y >= p.H) continue;
           for (int bk = 0; bk < 8; ++bk) {  // bk = block * 2 + K half
-            wait_relaxed(&wt_empty[st], ph);
+            wait_relaxed(&wt_empty[st], ph, p.wait_dem_ns);
             mbar_expect_tx(&wt_full[st], kWtStage);
             uint8_t* dst = smem_wt + st * kWtStage;
             bulk_load_1d(dst, reinterpret_cast<const uint8_t*>(p.wt) + ((size_t)(y & (kUp - 1)) * 8 + bk) * (2 * kWtPart), 2 * kWtPart, &wt_full[st]);
@@ -304,19 +308,19 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         uint8_t* frow_b = smem_f + fs_b * kFRow;
         if (y < 0 || y >= p.H) {
           // zero padding row of the head convolution (both parts)
-          wait_relaxed(&f_empty[fs_a], ph_a);
+          wait_relaxed(&f_empty[fs_a], ph_a, p.wait_build_ns);
           for (int k = (warp - 12) * 32 + lane; k < kFRow / 16; k += 256) reinterpret_cast<uint4*>(frow_a)[k] = make_uint4(0, 0, 0, 0);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&f_full[fs_a]);
-          wait_relaxed(&f_empty[fs_b], ph_b);
+          wait_relaxed(&f_empty[fs_b], ph_b, p.wait_build_ns);
           for (int k = (warp - 12) * 32 + lane; k < kFRow / 16; k += 256) reinterpret_cast<uint4*>(frow_b)[k] = make_uint4(0, 0, 0, 0);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&f_full[fs_b]);
           continue;
         }
-        wait_relaxed(d_full, dph);
+        wait_relaxed(d_full, dph, p.wait_build_ns);
         dph ^= 1;
         tc_fence_after();
         float v0[32], v1[32];
@@ -333,7 +337,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         const uint32_t off0 = (uint32_t)(lane >> 3) * kFPlane + (uint32_t)((lane & 7) >> 1) * 4 +
                               (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q) * 16;
         uint32_t low[kCells];
-        wait_relaxed(&f_empty[fs_a], ph_a);
+        wait_relaxed(&f_empty[fs_a], ph_a, p.wait_build_ns);
 #pragma unroll
         for (int c = 0; c < kCells; ++c) {
           const uint32_t wa = split16(act_fn<ACT_T>(fmaf(v0[c], sc, bias), p.alpha_t));   // block 2 gb, own channel
@@ -346,7 +350,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&f_full[fs_a]);
-        wait_relaxed(&f_empty[fs_b], ph_b);
+        wait_relaxed(&f_empty[fs_b], ph_b, p.wait_build_ns);
 #pragma unroll
         for (int c = 0; c < kCells; ++c) *reinterpret_cast<uint32_t*>(frow_b + off0 + c * (kUp * 16)) = low[c];
         fence_proxy_async_smem();
@@ -374,7 +378,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
                                     : p.dem + ((size_t)it.img * p.H + (yok ? y : 0)) * kW;
         const int x_end = p.src.on ? (p.src.W - ox < kW ? p.src.W - ox : kW) : kW;
         const uint32_t dst = smem_u32(smem_dem + as * kDemRow);
-        wait_relaxed(&a2_empty[as], aph);
+        wait_relaxed(&a2_empty[as], aph, p.wait_dem_ns);
         for (int k = lane; k < kRowPx; k += 32) {
           const int x = k - 1;
           const bool ok = yok && x >= 0 && x < x_end;
@@ -394,7 +398,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
       bool zero_out = false;
       if (p.src.on) dem_norm_spec(p.src.stats + (size_t)it.img * 3, p_clip, dem_min, range_f, zero_out);
       for (int i = 0; i < it.rows + 2; ++i) {
-        wait_relaxed(&dem_full[as], ph);
+        wait_relaxed(&dem_full[as], ph, p.wait_dem_ns);
         if (p.src.on) {
           // raw raster values -> normalised DEM, in place; pixels outside the tile stay the convolution's zero padding
           const int y = it.y0 - 1 + i;
@@ -406,23 +410,19 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
           }
           __syncwarp();
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int px0 = g * 128 + lane * 4;
-          const float* drow = reinterpret_cast<const float*>(smem_dem + as * kDemRow) + px0;  // halo index of px0 - 1
-          uint32_t hl[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) hl[k] = split16(drow[k]);
-          uint4* dst = reinterpret_cast<uint4*>(smem_a2 + as * kA2Row) + px0;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint4 v;
-            v.x = __byte_perm(hl[e], hl[e + 1], 0x5410);      // hi(-1), hi(0)
-            v.y = __byte_perm(hl[e + 2], hl[e], 0x7610);      // hi(+1), lo(-1)
-            v.z = __byte_perm(hl[e + 1], hl[e + 2], 0x7632);  // lo(0), lo(+1)
-            v.w = 0u;
-            dst[e] = v;
-          }
+        // consecutive lanes take consecutive pixels: every LDS / STS.128 of the warp is conflict-free (a lane-owns-4-pixels
+        // mapping made each 16-byte store a 16-way bank conflict: 12 % of the kernel's LSU wavefronts in the ncu capture)
+#pragma unroll 4
+        for (int g = 0; g < kW / 32; ++g) {
+          const int px = g * 32 + lane;
+          const float* drow = reinterpret_cast<const float*>(smem_dem + as * kDemRow) + px;  // halo index of px - 1
+          const uint32_t h0 = split16(drow[0]), h1 = split16(drow[1]), h2 = split16(drow[2]);
+          uint4 v;
+          v.x = __byte_perm(h0, h1, 0x5410);  // hi(-1), hi(0)
+          v.y = __byte_perm(h2, h0, 0x7610);  // hi(+1), lo(-1)
+          v.z = __byte_perm(h1, h2, 0x7632);  // lo(0), lo(+1)
+          v.w = 0u;
+          reinterpret_cast<uint4*>(smem_a2 + as * kA2Row)[px] = v;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -550,7 +550,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         const int slot = r % 3;
         const uint32_t par = (r / 3) & 1;
         for (int s = grp; s < kStrips; s += 2) {
-          wait_relaxed(&slot_full[s * 3 + slot], par);
+          wait_relaxed(&slot_full[s * 3 + slot], par, p.wait_epi_ns);
           tc_fence_after();
           const uint32_t taddr = lane_addr + s * (3 * kC) + slot * kC;
           float v[kC];
@@ -649,6 +649,18 @@ void launch_fused_x3(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfl
   p.alpha_h = alpha_h;
   p.scale_t_inv = scale_t_inv;
   p.scale_h_inv = scale_h_inv;
+  // FSR_X3_WAIT_NS="epilogue,builders,dem" overrides the suspend-time hints (A/B measurements)
+  p.wait_epi_ns = 400u;
+  p.wait_build_ns = 200u;
+  p.wait_dem_ns = 400u;
+  if (const char* e = getenv("FSR_X3_WAIT_NS")) {
+    unsigned a = 0, b = 0, c = 0;
+    if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3 && a && b && c) {
+      p.wait_epi_ns = a;
+      p.wait_build_ns = b;
+      p.wait_dem_ns = c;
+    }
+  }
   p.max_depth = max_depth;
   p.denom = denom;
   p.hw = hw_pack;

@@ -312,9 +312,10 @@ def test_run_raster_properties_at_mersch_size(engine):
     assert np.array_equal(out1[:384, :384], hard[:384, :384])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32"])
 def test_in_kernel_dem_normalisation_is_bit_identical_to_the_materialised_tiles(h1_model_fp, monkeypatch, precision):
-    """By default the fused high-resolution kernel normalises each tile's raster window itself (no dem_norm tensor in HBM);
+    """In the fp32 mode the fused high-resolution kernel normalises each tile's raster window itself (no dem_norm tensor in HBM;
+    the 16-bit kernel's rows are too short to hide the divisions, that mode keeps the materialised tiles);
     FSR_NO_LAZY_DEM=1 keeps the normalisation kernel's materialised tiles.  Same operation sequence -> same bits: ragged
     raster (zero padding beyond the raster), nodata replacement, caller-supplied statistics with a negative minimum."""
     from floodsr_b200.engine import EngineB200
