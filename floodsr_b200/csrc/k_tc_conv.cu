@@ -1067,8 +1067,8 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   // <= 16 pixels with enough CTAs left to fill the SMs.  Larger maps have short K loops and many CTAs; there two
   // co-resident single-tile CTAs (8 epilogue warps per SM instead of 4) win.  env FSR_NO_CONV_PAIR disables it.
   const long long n_single = (long long)p.tiles_x * p.tiles_y * tiles_n * ceil_div(cout, BN);
-  p.pair = (tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR") &&
-            (parts == 1 || 2 * BN * (p.nacc + 1) <= 512)) ? kConvPairs : 1;
+  // (split mode: no H1-family layer has both a <= 16-pixel map and a tile narrow enough for two M tiles' accumulators in TMEM)
+  p.pair = (parts == 1 && tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR")) ? kConvPairs : 1;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * ceil_div(tiles_n, p.pair)), (unsigned)ceil_div(cout, BN));
   if (BN == 128) {
     static bool attr = false;
@@ -1088,12 +1088,10 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
     p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && p.pair * 64 * (p.nacc + 1) > 256);
-    if (parts == 2 && p.pair == 2) launch_pdl(conv_tc_kernel<64, 2, 2>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
-    else if (parts == 2) launch_pdl(conv_tc_kernel<64, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
+    if (parts == 2) launch_pdl(conv_tc_kernel<64, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
     else if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<64, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else {
@@ -1102,12 +1100,10 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       attr = true;
     }
     p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && p.pair * 32 * (p.nacc + 1) > 256);
-    if (parts == 2 && p.pair == 2) launch_pdl(conv_tc_kernel<32, 2, 2>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
-    else if (parts == 2) launch_pdl(conv_tc_kernel<32, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
+    if (parts == 2) launch_pdl(conv_tc_kernel<32, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
     else if (p.pair == 2) launch_pdl(conv_tc_kernel<32, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<32>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<32, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);
   }

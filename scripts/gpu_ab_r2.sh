@@ -14,15 +14,7 @@ except Exception as exc:
     print(f"AB {name:14s} FAILED {exc}")
 PY
 }
-run default FSR_DUMMY=1
-run wait96 FSR_X3_WAIT_NS=96,96,96
-run wait1000 FSR_X3_WAIT_NS=1000,400,1000
-run wait2000 FSR_X3_WAIT_NS=2000,1000,2000
-run chain24 FSR_X3_CHAIN=24
-run chain96 FSR_X3_CHAIN=96
-run nopair FSR_NO_CONV_PAIR=1
-for c in 48 96; do
-  FSR_X3_CHAIN=$c timeout 300 python tests/x3_error_budget.py --modes fp32 --out gpurun_out/x3_error_budget_chain$c.txt > /dev/null 2>&1
-  grep "==" gpurun_out/x3_error_budget_chain$c.txt
-  awk '{ if ($0 ~ /err/) print }' gpurun_out/x3_error_budget_chain$c.txt | sort -t'r' -k3 | tail -0
+for v in "$@"; do
+  name=${v%%:*}; envs=${v#*:}
+  run $name $envs
 done
