@@ -189,14 +189,10 @@ void Engine::tc_prepare(const float* w) {
       {
         // wide, shallow levels run the persistent row-box kernel, which works on 32-channel groups
         const auto& d = tensors_[op.dst];
-        // (split mode: weights and halo boxes are twice as large; 16-channel groups keep the wider layers in shared memory)
-        for (int kc_rows : {kc > 4 ? 4 : kc, 2}) {
-          if (kc_rows > kc || t.rows || getenv("FSR_NO_CONV_ROWS") || tc_im_[op.dst]) continue;
-          if (kc_rows == 2 && (parts_ != 2 || getenv("FSR_X3_NO_ROWS16"))) continue;
-          if (conv_rows_ok(d.h, d.w, op.k, op.cout, C0, C1, kc_rows, parts_)) {
-            kc = kc_rows;
-            t.rows = true;
-          }
+        const int kc_rows = kc > 4 ? 4 : kc;
+        if (!getenv("FSR_NO_CONV_ROWS") && !tc_im_[op.dst] && conv_rows_ok(d.h, d.w, op.k, op.cout, C0, C1, kc_rows, parts_)) {
+          kc = kc_rows;
+          t.rows = true;
         }
       }
       t.kc = kc;

@@ -1132,8 +1132,13 @@ bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc, int p
   int pitch, box_rows, tiles_per_img;
   conv_rows_geometry(H, W, pitch, box_rows, tiles_per_img);
   const size_t w_bytes = (size_t)parts * 9 * ((C0 + C1) / 8) * cout * 16;
-  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + 3 * conv_rows_stage_bytes(kc * parts, box_rows, pitch) + 512;  // >= 3 stages
-  return smem <= 200 * 1024;
+  // The two MMA-issuing warps work on consecutive tiles at once and wait on ring positions up to one tile ahead of what the
+  // other has consumed: a parity wait is only meaningful within one lap of the ring, so both tiles' boxes must fit in it
+  // (a 16-channel-group variant for the wider split-mode layers violated this and read boxes before they had landed).
+  const size_t groups = (size_t)((C0 + C1) / 8) / kc;
+  const size_t need = std::max<size_t>(3, kRowsIssuers * groups);
+  const size_t smem = ((w_bytes + 1023) & ~(size_t)1023) + need * conv_rows_stage_bytes(kc * parts, box_rows, pitch) + 512;
+  return need <= (size_t)kRowMaxStages && smem <= 200 * 1024;
 }
 
 void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
