@@ -23,6 +23,8 @@ Pinning status:
 * network forward (a10): PARITY UNPINNED.  onnxruntime (pinned 1.24.2 / 1.22.2 by the reference's
   containers) and the `model_infer.onnx` release asset are absent offline and the reference holds no
   per-pixel golden output.  The interpreter is cross-checked against OpenCV's independent ONNX importer
-  (`cv2.dnn.readNetFromONNX`) on the random-init H1 graph, and parity tests try a live onnxruntime
-  session first whenever one is importable.
+  (`cv2.dnn.readNetFromONNX`) on the random-init H1 graph (`tests/test_forward_pin.py`), and
+  `oracle.engine_ref.OracleEngine(backend="auto")` -- what every parity test and bench.py's CPU legs build --
+  opens a live onnxruntime session (the reference's own call, ort.py:54,193) whenever onnxruntime is
+  importable and reports which backend ran in `.backend`.
 """
