@@ -17,6 +17,7 @@ FSR_OK, FSR_E_INVALID, FSR_E_CUDA, FSR_E_ASSERT, FSR_E_UNSUPPORTED = 0, -1, -2, 
 PREC_FP32, PREC_FP16, PREC_FP32_SIMT = 0, 2, 3
 WINDOW_HARD, WINDOW_FEATHER = 0, 1
 FLAG_DEPTH_NONFINITE, FLAG_DEM_NONFINITE, FLAG_DEM_FLAT_NONZERO, FLAG_DEPTH_NOT_UNIT, FLAG_DEM_NOT_UNIT = 1, 2, 4, 8, 16
+FLAG_PRED_NONFINITE = 32
 PROF_CATEGORIES = ("normalize", "lr_conv", "lr_misc", "convt", "head", "invert", "blend")
 
 

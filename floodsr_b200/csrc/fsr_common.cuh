@@ -139,6 +139,23 @@ struct TileGrid {
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// SM count of the CURRENT device (grid caps, wave sizing): looked up per device, not per process
+inline int current_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cache[dev] && cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cache[dev] = 148;
+  return cache[dev];
+}
+// one-time per-device action (function attributes are per device): true the first time it is asked for (key, device)
+inline bool first_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   if (act == FSR_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == FSR_ACT_LEAKY) return v > 0.0f ? v : v * alpha;

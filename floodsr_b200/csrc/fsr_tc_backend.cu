@@ -53,7 +53,7 @@ void fused_pack_convt(const float* w, uint16_t* dst, uint16_t (*cvt)(float));
 void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfloat16* wt_pack, const float* bias_t, int act_t,
                         float alpha_t, const __nv_bfloat16* hw_pack, const float* w2, const float* b2, int act_h, float alpha_h,
                         const float* dem, const DemSource& src, float* pred_m, float* pred_norm, int n_img, int H, float max_depth,
-                        float denom, int half, int n_sms, cudaStream_t s);
+                        float denom, int half, int n_sms, unsigned* flags, cudaStream_t s);
 
 // split-operand (fp32-tolerance) variant of the fused kernel: k_tc_fused_x3.cu
 bool fused_x3_ok(int H, int W, int lr_h, int lr_w, int cin_t, int cout_t, int k_t, int cmid, int ksz);
@@ -64,7 +64,7 @@ void fused_x3_pack_convt(const float* w, float scale, uint16_t* dst);
 void launch_fused_x3(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfloat16* wt_pack, const float* bias_t, float scale_t_inv,
                      int act_t, float alpha_t, const __nv_bfloat16* hw_pack, const float* bias_h, float scale_h_inv, const float* w2,
                      const float* b2, int act_h, float alpha_h, const float* dem, const DemSource& src, float* pred_m, float* pred_norm,
-                     int n_img, int H, float max_depth, float denom, int n_sms, cudaStream_t s);
+                     int n_img, int H, float max_depth, float denom, int n_sms, unsigned* flags, cudaStream_t s);
 
 static bool g_pack_half = false;  // 16-bit format used while packing weights (set by tc_prepare)
 static inline uint16_t f2bf(float f) {
@@ -361,12 +361,12 @@ void Engine::tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, 
     launch_fused_x3(reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]), tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(),
                     fused_bias_t_.data(), fused_scale_t_inv_, ct.act, ct.alpha, fused_hw_.as<__nv_bfloat16>(), fused_bias_h_.data(),
                     fused_scale_h_inv_, th.h_w2.data(), &th.h_b2, hd.act, hd.alpha, tbase_[1], dem_src_, pm, pn, n, tf.h, max_depth, denom,
-                    n_sms_, s);
+                    n_sms_, d_flags(), s);
     return;
   }
   launch_fused_hr_tc(reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]), tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(),
                      fused_bias_t_.data(), ct.act, ct.alpha, fused_hw_.as<__nv_bfloat16>(), th.h_w2.data(), &th.h_b2, hd.act, hd.alpha,
-                     tbase_[1], dem_src_, pm, pn, n, tf.h, max_depth, denom, half, n_sms_, s);
+                     tbase_[1], dem_src_, pm, pn, n, tf.h, max_depth, denom, half, n_sms_, d_flags(), s);
 }
 
 void Engine::tc_ensure_arena(int cap) {

@@ -196,7 +196,7 @@ void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, in
       // row pair -> 0.43); env FSR_BLEND_BLOCKS overrides
       const int gx = ceil_div(g.W / 4, 256);
       static const int per_sm = getenv("FSR_BLEND_BLOCKS") ? atoi(getenv("FSR_BLEND_BLOCKS")) : 32;
-      const int gy = std::min(ceil_div(nr, R), std::max(1, (148 * per_sm) / gx));
+      const int gy = std::min(ceil_div(nr, R), std::max(1, (current_sm_count() * per_sm) / gx));
       dim3 grid((unsigned)gx, (unsigned)gy);
       blend_fast_kernel<R><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp);
     } else if (vec) {

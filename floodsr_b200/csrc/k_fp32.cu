@@ -225,7 +225,7 @@ __global__ void invert_depth_kernel(const float* __restrict__ pred_norm, float* 
 
 static inline int grid_for(size_t total, int threads = 256) {
   size_t b = (total + threads - 1) / threads;
-  const size_t cap = 148 * 32;
+  const size_t cap = (size_t)current_sm_count() * 32;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 

@@ -508,11 +508,9 @@ void launch_tile_normalize(const float* d_dem, const float* d_depth, const TileG
   if (n_tiles <= 0) return;
   FSR_REQUIRE(T % 4 == 0 && T * (T / 4) % kThreads == 0, "hr tile must be a multiple of 64 pixels");
   if (p.normalize_inputs) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    if (first_on_device(attr))
       FSR_CUDA(cudaFuncSetAttribute(tile_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * (int)sizeof(unsigned)));
-      attr = true;
-    }
     tile_normalize_kernel<<<n_tiles, kThreads, kCap * sizeof(unsigned), stream>>>(d_dem, d_depth, grid, tile_base, T, TL, scale, p,
                                                                                  d_dem_norm, d_depth_norm, d_stats, d_dem_lr, d_flags);
   } else {

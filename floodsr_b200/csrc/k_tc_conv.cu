@@ -886,7 +886,7 @@ __global__ void cp8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float*
 
 inline int grid_for(long long total, int threads = 256) {
   long long b = (total + threads - 1) / threads;
-  const long long cap = 148 * 16;
+  const long long cap = (long long)current_sm_count() * 16;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -898,7 +898,7 @@ template <int BN>
 int conv_stages(int kc, int n_iters, long long n_ctas, int pair, bool one_cta_per_sm = false) {
   // few CTAs (deep, narrow levels): one CTA per SM with a deep ring, each K step is L2-latency bound;
   // many CTAs: keep two or more CTAs per SM so that their prologues and epilogues overlap
-  const size_t budget = (one_cta_per_sm || n_ctas <= (pair > 1 ? 148 : 2 * 148)) ? 200 * 1024 : 100 * 1024;
+  const size_t budget = (one_cta_per_sm || n_ctas <= (pair > 1 ? current_sm_count() : 2 * current_sm_count())) ? 200 * 1024 : 100 * 1024;
   int st = (int)(budget / ((size_t)pair * kc * 128 * 16 + (size_t)kc * BN * 16));
   st = st > kMaxStages ? kMaxStages : st;
   st = st > n_iters ? n_iters : st;
@@ -1071,36 +1071,33 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   p.pair = (parts == 1 && tiles_n >= 2 && n_single >= 256 && p.tiles_x * p.tiles_y <= 16 && !getenv("FSR_NO_CONV_PAIR")) ? kConvPairs : 1;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * ceil_div(tiles_n, p.pair)), (unsigned)ceil_div(cout, BN));
   if (BN == 128) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    if (first_on_device(attr)) {
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      attr = true;
     }
     p.stages = conv_stages<128>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2);
     if (parts == 2) launch_pdl(conv_tc_kernel<128, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
     else if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<128, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else if (BN == 64) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    if (first_on_device(attr)) {
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      attr = true;
     }
     p.stages = conv_stages<64>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && p.pair * 64 * (p.nacc + 1) > 256);
     if (parts == 2) launch_pdl(conv_tc_kernel<64, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
     else if (p.pair == 2) launch_pdl(conv_tc_kernel<64, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<64>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<64, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<64>(kc * parts, p.stages, 1), s, m0, m1, p);
   } else {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    if (first_on_device(attr)) {
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-      attr = true;
     }
     p.stages = conv_stages<32>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && p.pair * 32 * (p.nacc + 1) > 256);
     if (parts == 2) launch_pdl(conv_tc_kernel<32, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<32>(kc * parts, p.stages, 1), s, m0, m1, p);

@@ -76,6 +76,7 @@ struct FusedParams {
   DemSource src;        // or: the raw raster + per-tile statistics (src.on == 1)
   float* pred_m;        // [N][H][512]
   float* pred_norm;     // or nullptr
+  unsigned* flags;      // FSR_FLAG_PRED_NONFINITE is raised here
   float bias_t[kC];     // convT bias
   float w2[kC];         // 1x1 projection
   float b2;
@@ -521,6 +522,7 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
           }
           const float out = (o0 + o1) + (o2 + o3);
           const size_t off = ((size_t)it.img * p.H + (it.y0 + j)) * kW + s * 128 + m;
+          if (!(fabsf(out) <= 3.0e38f)) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);  // Inf / NaN: never in a healthy run
           if (p.pred_norm) p.pred_norm[off] = out;
           const float yn = fminf(fmaxf(out, 0.0f), 1.0f);
           p.pred_m[off] = fminf(fmaxf(expm1f(__fmul_rn(yn, p.denom)), 0.0f), p.max_depth);
@@ -591,7 +593,7 @@ void fused_pack_convt(const float* w, uint16_t* dst, uint16_t (*cvt)(float)) {
 void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfloat16* wt_pack, const float* bias_t, int act_t,
                         float alpha_t, const __nv_bfloat16* hw_pack, const float* w2, const float* b2, int act_h, float alpha_h,
                         const float* dem, const DemSource& src, float* pred_m, float* pred_norm, int n_img, int H, float max_depth,
-                        float denom, int half, int n_sms, cudaStream_t s) {
+                        float denom, int half, int n_sms, unsigned* flags, cudaStream_t s) {
   FusedParams p{};
   p.H = H;
   p.N = n_img;
@@ -608,6 +610,7 @@ void launch_fused_hr_tc(const __nv_bfloat16* lr, long long lr_plane, const __nv_
   p.src = src;
   p.pred_m = pred_m;
   p.pred_norm = pred_norm;
+  p.flags = flags;
   for (int c = 0; c < kC; ++c) {
     p.bias_t[c] = bias_t ? bias_t[c] : 0.0f;
     p.w2[c] = w2[c];

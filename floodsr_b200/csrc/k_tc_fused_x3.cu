@@ -71,6 +71,7 @@ struct X3Params {
   DemSource src;        // or: the raw raster + per-tile statistics (src.on == 1)
   float* pred_m;        // [N][H][512]
   float* pred_norm;     // or nullptr
+  unsigned* flags;      // FSR_FLAG_PRED_NONFINITE is raised here
   float bias_t[kC];     // convT bias
   float bias_h[kC];     // head conv3x3 bias
   float w2[kC];         // 1x1 projection
@@ -571,6 +572,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
           }
           const float out = (o0 + o1) + (o2 + o3);
           const size_t off = ((size_t)it.img * p.H + (it.y0 + j)) * kW + s * 128 + m;
+          if (!(fabsf(out) <= 3.0e38f)) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);  // Inf / NaN: never in a healthy run
           if (p.pred_norm) p.pred_norm[off] = out;
           const float yn = fminf(fmaxf(out, 0.0f), 1.0f);
           p.pred_m[off] = fminf(fmaxf(expm1f(__fmul_rn(yn, p.denom)), 0.0f), p.max_depth);
@@ -640,7 +642,7 @@ void fused_x3_pack_convt(const float* w, float scale, uint16_t* dst) {
 void launch_fused_x3(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfloat16* wt_pack, const float* bias_t, float scale_t_inv,
                      int act_t, float alpha_t, const __nv_bfloat16* hw_pack, const float* bias_h, float scale_h_inv, const float* w2,
                      const float* b2, int act_h, float alpha_h, const float* dem, const DemSource& src, float* pred_m, float* pred_norm,
-                     int n_img, int H, float max_depth, float denom, int n_sms, cudaStream_t s) {
+                     int n_img, int H, float max_depth, float denom, int n_sms, unsigned* flags, cudaStream_t s) {
   X3Params p{};
   p.H = H;
   p.N = n_img;
@@ -669,6 +671,7 @@ void launch_fused_x3(const __nv_bfloat16* lr, long long lr_plane, const __nv_bfl
   p.src = src;
   p.pred_m = pred_m;
   p.pred_norm = pred_norm;
+  p.flags = flags;
   for (int c = 0; c < kC; ++c) {
     p.bias_t[c] = bias_t ? bias_t[c] : 0.0f;
     p.bias_h[c] = bias_h ? bias_h[c] : 0.0f;

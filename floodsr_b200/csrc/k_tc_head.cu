@@ -223,13 +223,13 @@ void launch_convt_tc(const __nv_bfloat16* src, long long plane_in, const __nv_bf
   p.out = dst;
   const int m_tiles = p.tiles_x * p.tiles_y * ceil_div(n_img, p.bn);
   // enough CTAs to fill the 148 SMs about twice; each CTA keeps its A tile and loops over its N tiles
-  int groups = ceil_div(2 * 148, m_tiles);
+  int groups = ceil_div(2 * current_sm_count(), m_tiles);
   groups = groups < 1 ? 1 : (groups > p.n_tiles_total ? p.n_tiles_total : groups);
   p.n_tiles_per_cta = ceil_div(p.n_tiles_total, groups);
   groups = ceil_div(p.n_tiles_total, p.n_tiles_per_cta);
   CUtensorMap mA = make_cp8_tensor_map(src, Win, Hin, n_img, cin / 8, plane_in, p.bw, p.bh, p.bn, cin / 8);
-  static bool attr = false;
-  if (!attr) { FSR_CUDA(cudaFuncSetAttribute(convt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)convt_smem_bytes())); attr = true; }
+  static bool attr[64] = {false};
+  if (first_on_device(attr)) FSR_CUDA(cudaFuncSetAttribute(convt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)convt_smem_bytes()));
   dim3 grid((unsigned)m_tiles, (unsigned)groups);
   convt_tc_kernel<<<grid, kCtThreads, convt_smem_bytes(), s>>>(mA, p);
   FSR_LAUNCH_CHECK();

@@ -236,6 +236,10 @@ class EngineB200(EngineBase):
             if bad is not None:
                 raise AssertionError(f"DEM range must be > 0; got min={float(bad[1])}, max={float(bad[2])}")
             raise AssertionError("DEM range must be > 0")
+        if flags & _lib.FLAG_PRED_NONFINITE:
+            raise FloatingPointError(
+                "the network produced non-finite values (a 16-bit activation overflowed, or the weights are not finite); "
+                "the reference's clip would hide them as 0 m -- use precision='fp32' or check the model file")
         raise AssertionError(f"device-side input validation failed (flags={flags:#x})")
 
     def _call(self, code: int, flags: C.c_uint32, normalize_inputs: bool, stats: np.ndarray | None) -> None:

@@ -55,6 +55,8 @@ extern "C" {
 #define FSR_FLAG_DEM_FLAT_NONZERO 4u /* preprocessing.py:82 "DEM range must be > 0" */
 #define FSR_FLAG_DEPTH_NOT_UNIT 8u  /* ort.py:171  (normalize_inputs=False) */
 #define FSR_FLAG_DEM_NOT_UNIT 16u   /* ort.py:174  */
+#define FSR_FLAG_PRED_NONFINITE 32u /* the network produced Inf / NaN (a 16-bit activation overflowed, or the weights hold
+                                       non-finite values): the clip of preprocessing.py:161 would otherwise hide it as 0 m */
 
 typedef struct fsr_engine fsr_engine;
 

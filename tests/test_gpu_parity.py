@@ -388,6 +388,26 @@ def test_bilinear_asymmetric_resize_on_the_engine(tmp_path, ctm):
     _engine_vs_oracle_on_model(fp, "fp32", 1e-5)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_activation_overflow_is_reported_not_clipped_to_zero(tmp_path, precision):
+    """Both tensor-core modes keep activations in fp16 (pairs): a network whose activations exceed 65504 produces Inf / NaN,
+    which the final clip would turn into 0 m.  The engine raises instead (FSR_FLAG_PRED_NONFINITE)."""
+    from floodsr_b200.engine import EngineB200
+    from floodsr_b200.h1 import build_h1_model
+    from floodsr_b200.onnx_io import save_onnx
+
+    m = build_h1_model(seed=0)
+    name = next(n.inputs[1] for n in m.nodes if n.op_type == "Conv" and m.initializers[n.inputs[1]].shape[:2] == (32, 32))
+    m.initializers[name] = (m.initializers[name] * np.float32(3e5)).astype(np.float32)
+    fp = tmp_path / "overflow.onnx"
+    save_onnx(m, fp)
+    eng = EngineB200(fp, precision=precision)
+    depth, dem = synth_tile(1)
+    with pytest.raises(FloatingPointError, match="non-finite"):
+        eng.run_tile(depth, dem)
+    eng.close()
+
+
 @pytest.mark.parametrize("f", [16, 64])
 def test_other_widths_run_with_the_fp32_high_resolution_pair(tmp_path, f):
     """base_filters 16 / 64: the low-resolution layers stay on tcgen05 (16-channel outputs, 1024-channel deep level), the

@@ -50,6 +50,17 @@ def test_postprocess_depth_clip_and_mask():
     assert postprocess_depth(x, 5.0, 1e-3).tolist() == [[0.0, 0.0, np.float32(0.001), 0.5, 5.0]]
 
 
+def _assert_close_except_mask_flips(got, want, want_unmasked, tol=1e-4):
+    """<= `tol` m wherever the 1 mm mask (ResUNet_16x_DEM.py:575-583) agrees; a pixel may only change its masked / unmasked
+    state if the oracle's unmasked value lies within `tol` of the 1 mm threshold, and then it differs by < 1 mm + tol."""
+    flips = (got == 0) != (want == 0)
+    assert np.abs(got - want)[~flips].max() <= tol
+    if flips.any():
+        assert np.abs(want_unmasked[flips] - 1e-3).max() <= tol
+        assert np.abs(got - want)[flips].max() <= 1e-3 + tol
+    assert flips.mean() < 1e-4
+
+
 @pytest.mark.gpu
 def test_worker_run_prepared_matches_oracle(h1_model_fp):
     from floodsr_b200.worker import ModelWorkerB200
@@ -58,7 +69,8 @@ def test_worker_run_prepared_matches_oracle(h1_model_fp):
 
     depth, dem = synth_raster(976, 1104, seed=5)
     want, n_tiles, summary = run_tiled(OracleEngine(h1_model_fp), depth, dem, window_method="feather", overlap_lr=8)
-    want = np.where(np.clip(want, 0.0, 5.0) < 1e-3, 0.0, np.clip(want, 0.0, 5.0)).astype(np.float32)
+    want_unmasked = np.clip(want, 0.0, 5.0)
+    want = np.where(want_unmasked < 1e-3, 0.0, want_unmasked).astype(np.float32)
     with ModelWorkerB200(h1_model_fp, precision="fp32") as worker:
         res = worker.run_prepared(depth, dem)
         assert worker.engine is not None
@@ -68,8 +80,7 @@ def test_worker_run_prepared_matches_oracle(h1_model_fp):
     assert pre["input_shape"]["output_shape"] == [976, 1104]
     got = res["prediction_m"]
     assert got.dtype == np.float32 and got.shape == want.shape
-    assert np.abs(got - want).max() <= 1e-3  # 1e-4 m model tolerance; a pixel at the 1 mm mask edge may flip to 0
-    assert ((got == 0) != (want == 0)).mean() < 1e-4
+    _assert_close_except_mask_flips(got, want, want_unmasked)
 
 
 @pytest.mark.gpu
@@ -92,7 +103,8 @@ def test_worker_run_raw_grids_matches_oracle_composition(h1_model_fp):
     dem_model = np.where(np.isclose(dem_model, -9999.0), 0.0, dem_model).astype(np.float32)
     pred_model, n_tiles, _ = run_tiled(OracleEngine(h1_model_fp), depth, dem_model, window_method="feather", overlap_lr=8)
     want = resample_bilinear(pred_model, t_model, (960, 960), t_raw)
-    want = np.where(np.clip(want, 0.0, 5.0) < 1e-3, 0.0, np.clip(want, 0.0, 5.0)).astype(np.float32)
+    want_unmasked = np.clip(want, 0.0, 5.0)
+    want = np.where(want_unmasked < 1e-3, 0.0, want_unmasked).astype(np.float32)
     with ModelWorkerB200(h1_model_fp, precision="fp32") as worker:
         res = worker.run_raw_grids(depth, bounds, dem_raw, t_raw, dem_nodata=-9999.0)
     pre = res["preprocess"]
@@ -100,5 +112,4 @@ def test_worker_run_raw_grids_matches_oracle_composition(h1_model_fp):
     assert pre["input_shape"]["output_shape"] == [960, 960] and pre["input_shape"]["model_space_crop_height"] == 1024
     got = res["prediction_m"]
     assert got.dtype == np.float32 and got.shape == (960, 960)
-    assert np.abs(got - want).max() <= 1e-3
-    assert ((got == 0) != (want == 0)).mean() < 1e-4
+    _assert_close_except_mask_flips(got, want, want_unmasked)
