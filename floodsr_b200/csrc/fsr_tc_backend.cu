@@ -20,12 +20,12 @@ int conv_tc_bn(int cout, int parts, int hh_steps);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
-                    int parts, float out_scale, int cpad_out, cudaStream_t s);
+                    int parts, float out_scale, int cpad_out, unsigned* flags, cudaStream_t s);
 bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc, int parts);
 void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                          const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                          long long plane_out, int n_img, int H, int W, int cout, int act, float alpha, int half, int n_sms,
-                         int parts, float out_scale, cudaStream_t s);
+                         int parts, float out_scale, unsigned* flags, cudaStream_t s);
 void launch_pack_small(const float* s0, int c0, const float* s1, int c1, __nv_bfloat16* dst, long long n_pix, long long plane,
                        int chunks, int half, int parts, cudaStream_t s);
 void launch_pool_cp8(const __nv_bfloat16* src, __nv_bfloat16* dst, int chunks, int n_img, int Hin, int Win, int k, int mode,
@@ -540,11 +540,11 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
         }
         if (tc.rows)
           launch_conv_rows_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res),
-                              cp8(op.dst), tc_plane(op.dst), n, td.h, td.w, op.cout, op.act, op.alpha, half, n_sms_, parts, tc.out_scale, s);
+                              cp8(op.dst), tc_plane(op.dst), n, td.h, td.w, op.cout, op.act, op.alpha, half, n_sms_, parts, tc.out_scale, d_flags(), s);
         else
           launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
                          tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, tc_im_[op.dst], parts, tc.out_scale,
-                         tc_cpad_[op.dst], s);
+                         tc_cpad_[op.dst], d_flags(), s);
         break;
       }
       case FSR_OP_POOL:

@@ -65,6 +65,16 @@ __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t
 __device__ __forceinline__ uint32_t desc_lo32(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
 constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
 
+// Activations are stored as fp16 (pairs): a value beyond 65504 would become Inf, turn into NaN in the next layer and be
+// swallowed by the next fmaxf-ReLU -- the result would be silently wrong.  Every convolution epilogue therefore tests what it
+// is about to store; the engine turns the flag into an error (the fp32 reference would have carried on with finite numbers).
+__device__ __forceinline__ void flag_unstorable(const float (&v)[8], unsigned* flags) {
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bad |= !(fabsf(v[i]) <= 65504.0f);
+  if (bad) atomicOr(flags, FSR_FLAG_PRED_NONFINITE);
+}
+
 struct ConvTcParams {
   int H, W, N;             // per-image extent and number of images in this launch
   int bw, bh, bn;          // M-tile box (bw*bh*bn == 128)
@@ -92,6 +102,7 @@ struct ConvTcParams {
   const float* bias;           // [cout] or nullptr
   const __nv_bfloat16* res;    // CP8 residual or nullptr
   __nv_bfloat16* out;          // CP8 output
+  unsigned* flags;             // FSR_FLAG_PRED_NONFINITE: an output does not fit fp16 (|v| > 65504, Inf or NaN)
 };
 
 template <int BN, int PAIR, int PARTS>
@@ -305,6 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * p.alpha;
           }
+          flag_unstorable(v, p.flags);
           if (PARTS == 2) {
             uint4 hi, lo;
             split_x8(v, hi, lo);
@@ -370,6 +382,7 @@ struct ConvRowsParams {
   const float* bias;
   const __nv_bfloat16* res;
   __nv_bfloat16* out;
+  unsigned* flags;     // FSR_FLAG_PRED_NONFINITE: an output does not fit fp16
 };
 
 template <int BN, int PARTS>
@@ -622,6 +635,7 @@ conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.0f ? o[i] : o[i] * p.alpha;
             }
+            flag_unstorable(o, p.flags);
             if (PARTS == 2) {
               uint4 hi, lo;
               split_x8(o, hi, lo);
@@ -1021,8 +1035,9 @@ int conv_tc_bn(int cout, int parts, int hh_steps) {
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
-                    int parts, float out_scale, int cpad_out, cudaStream_t s) {
+                    int parts, float out_scale, int cpad_out, unsigned* flags, cudaStream_t s) {
   ConvTcParams p{};
+  p.flags = flags;
   p.half = half;
   p.parts = parts;
   p.out_scale = parts == 2 ? out_scale : 1.0f;
@@ -1141,8 +1156,9 @@ bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc, int p
 void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                          const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                          long long plane_out, int n_img, int H, int W, int cout, int act, float alpha, int half, int n_sms,
-                         int parts, float out_scale, cudaStream_t s) {
+                         int parts, float out_scale, unsigned* flags, cudaStream_t s) {
   ConvRowsParams p{};
+  p.flags = flags;
   p.parts = parts;
   p.sets = parts == 2 ? 2 : kRowsEpiSets;  // split mode: 2 buffers x (nacc + 1) accumulators x cout columns = 512
   p.nacc = parts == 2 ? (cout == 64 ? 3 : 7) : 1;

@@ -318,16 +318,19 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
           // lanes 2k / 2k+1 hold channels 2k / 2k+1: one shuffle per cell lets the even lane store the channel pair of block
           // 2 gb and the odd lane that of block 2 gb + 1 as 32-bit words (32 lanes -> 32 distinct banks)
           const bool odd = lane & 1;
+          bool bad = false;  // a feature value that does not fit the 16-bit format (see flag_unstorable in k_tc_conv.cu)
           uint8_t* dst0 = frow + (uint32_t)(lane >> 3) * kFPlane + (uint32_t)((lane & 7) >> 1) * 4 +
                           (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q) * 16;
 #pragma unroll
           for (int c = 0; c < kCells; ++c) {
             const float a = act_fn<ACT_T>(v0[c] + bias, p.alpha_t);   // block 2 gb, own channel
             const float b = act_fn<ACT_T>(v1[c] + bias, p.alpha_t);   // block 2 gb + 1, own channel
+            bad |= !(fabsf(a) <= 65504.0f) | !(fabsf(b) <= 65504.0f);
             const float other = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
             const uint32_t w = odd ? pack_x2(other, b, HALF) : pack_x2(a, other, HALF);
             *reinterpret_cast<uint32_t*>(dst0 + c * (kUp * 16)) = w;
           }
+          if (bad) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);
         }
         fence_proxy_async_smem();
         __syncwarp();

@@ -338,16 +338,20 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         const uint32_t off0 = (uint32_t)(lane >> 3) * kFPlane + (uint32_t)((lane & 7) >> 1) * 4 +
                               (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q) * 16;
         uint32_t low[kCells];
+        bool bad = false;  // a feature value that does not fit fp16 (see flag_unstorable in k_tc_conv.cu)
         wait_relaxed(&f_empty[fs_a], ph_a, p.wait_build_ns);
 #pragma unroll
         for (int c = 0; c < kCells; ++c) {
-          const uint32_t wa = split16(act_fn<ACT_T>(fmaf(v0[c], sc, bias), p.alpha_t));   // block 2 gb, own channel
-          const uint32_t wb = split16(act_fn<ACT_T>(fmaf(v1[c], sc, bias), p.alpha_t));   // block 2 gb + 1, own channel
+          const float fa = act_fn<ACT_T>(fmaf(v0[c], sc, bias), p.alpha_t), fb = act_fn<ACT_T>(fmaf(v1[c], sc, bias), p.alpha_t);
+          bad |= !(fabsf(fa) <= 65504.0f) | !(fabsf(fb) <= 65504.0f);
+          const uint32_t wa = split16(fa);   // block 2 gb, own channel
+          const uint32_t wb = split16(fb);   // block 2 gb + 1, own channel
           const uint32_t other = __shfl_xor_sync(0xffffffffu, odd ? wa : wb, 1);
           const uint32_t first = odd ? other : wa, second = odd ? wb : other;             // channels 2k, 2k + 1 of the stored block
           *reinterpret_cast<uint32_t*>(frow_a + off0 + c * (kUp * 16)) = __byte_perm(first, second, 0x5410);
           low[c] = __byte_perm(first, second, 0x7632);
         }
+        if (bad) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&f_full[fs_a]);

@@ -121,6 +121,7 @@ class EngineB200(EngineBase):
         handle = C.c_void_p()
         plan = (C.c_char * len(lowered.plan_bytes)).from_buffer_copy(lowered.plan_bytes)
         weights = np.ascontiguousarray(lowered.weights, dtype=np.float32)
+        assert np.isfinite(weights).all(), f"model weights contain non-finite values: {self._model_fp}"
         _lib.check(
             lib.fsr_create(
                 C.cast(plan, C.c_void_p), len(lowered.plan_bytes), _lib.fptr(weights), weights.size, self.device,
