@@ -7,11 +7,13 @@ missing library or a missing CUDA device is an error as soon as an engine is cre
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "libfloodsr_b200.so"
+# FLOODSR_B200_LIB selects another build of the same ABI (A/B measurements of kernel variants)
+LIB_PATH = Path(os.environ["FLOODSR_B200_LIB"]).resolve() if os.environ.get("FLOODSR_B200_LIB") else Path(__file__).resolve().parent / "libfloodsr_b200.so"
 
 FSR_OK, FSR_E_INVALID, FSR_E_CUDA, FSR_E_ASSERT, FSR_E_UNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_FP16, PREC_FP32_SIMT = 0, 2, 3

@@ -163,7 +163,8 @@ __device__ __forceinline__ float act_fn(float v, float alpha) {
 }
 
 template <int ACT, int ACT_T, int HALF>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)  // 80 registers: the register file is split per SM sub-partition (16 K each), which
+                                                // holds 6 of the 22 warps: 6 x 32 x 88 would not fit
 fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem_hw = smem_raw;                                  // head weights
@@ -318,19 +319,22 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
           // lanes 2k / 2k+1 hold channels 2k / 2k+1: one shuffle per cell lets the even lane store the channel pair of block
           // 2 gb and the odd lane that of block 2 gb + 1 as 32-bit words (32 lanes -> 32 distinct banks)
           const bool odd = lane & 1;
-          bool bad = false;  // a feature value that does not fit the 16-bit format (see flag_unstorable in k_tc_conv.cu)
+          __half2 hmax = __floats2half2_rn(0.0f, 0.0f);  // largest |value| stored (HALF): Inf = it did not fit fp16 (flag_unstorable, k_tc_conv.cu)
           uint8_t* dst0 = frow + (uint32_t)(lane >> 3) * kFPlane + (uint32_t)((lane & 7) >> 1) * 4 +
                           (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q) * 16;
 #pragma unroll
           for (int c = 0; c < kCells; ++c) {
             const float a = act_fn<ACT_T>(v0[c] + bias, p.alpha_t);   // block 2 gb, own channel
             const float b = act_fn<ACT_T>(v1[c] + bias, p.alpha_t);   // block 2 gb + 1, own channel
-            bad |= !(fabsf(a) <= 65504.0f) | !(fabsf(b) <= 65504.0f);
+
             const float other = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
             const uint32_t w = odd ? pack_x2(other, b, HALF) : pack_x2(a, other, HALF);
             *reinterpret_cast<uint32_t*>(dst0 + c * (kUp * 16)) = w;
+#ifndef FSR_NO_BUILDER_CHECK
+            if (HALF) hmax = __hmax2(hmax, __habs2(*reinterpret_cast<const __half2*>(&w)));  // one instruction per two values
+#endif
           }
-          if (bad) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);
+          if (__hisinf(__low2half(hmax)) || __hisinf(__high2half(hmax))) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -525,7 +529,9 @@ fused_hr_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__
           }
           const float out = (o0 + o1) + (o2 + o3);
           const size_t off = ((size_t)it.img * p.H + (it.y0 + j)) * kW + s * 128 + m;
+#ifndef FSR_NO_EPI_CHECK
           if (!(fabsf(out) <= 3.0e38f)) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);  // Inf / NaN: never in a healthy run
+#endif
           if (p.pred_norm) p.pred_norm[off] = out;
           const float yn = fminf(fmaxf(out, 0.0f), 1.0f);
           p.pred_m[off] = fminf(fmaxf(expm1f(__fmul_rn(yn, p.denom)), 0.0f), p.max_depth);

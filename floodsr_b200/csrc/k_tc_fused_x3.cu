@@ -157,7 +157,8 @@ __device__ __forceinline__ float act_fn(float v, float alpha) {
 }
 
 template <int ACT, int ACT_T>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)  // 80 registers: the register file is split per SM sub-partition (16 K each), which
+                                                // holds 6 of the 22 warps: 6 x 32 x 88 would not fit
 fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ X3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem_hw = smem_raw;                                  // head weights
@@ -337,21 +338,31 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         const bool odd = lane & 1;
         const uint32_t off0 = (uint32_t)(lane >> 3) * kFPlane + (uint32_t)((lane & 7) >> 1) * 4 +
                               (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q) * 16;
+        // The kernel's time follows the builders' instruction count (measured: +2 instructions per cell = +9 %), so a cell is
+        // ~16 instructions: PACKED conversions (one F2FP for the two blocks' values; scalar F2F runs on a quarter-rate pipe), one
+        // shuffle carrying the (hi, lo) the neighbouring lane needs, byte permutes instead of shifts and selects.  The even lane
+        // stores the channel pair (2k, 2k + 1) of block 2 gb, the odd lane that of block 2 gb + 1.
+        const uint32_t sel_send = odd ? 0x5410u : 0x7632u;
+        const uint32_t sel_hi = odd ? 0x3254u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7610u;
         uint32_t low[kCells];
-        bool bad = false;  // a feature value that does not fit fp16 (see flag_unstorable in k_tc_conv.cu)
+        __half2 hmax = __floats2half2_rn(0.0f, 0.0f);  // largest |hi| stored: Inf = a feature value that does not fit fp16 (see
+                                                       // flag_unstorable in k_tc_conv.cu)
         wait_relaxed(&f_empty[fs_a], ph_a, p.wait_build_ns);
 #pragma unroll
         for (int c = 0; c < kCells; ++c) {
           const float fa = act_fn<ACT_T>(fmaf(v0[c], sc, bias), p.alpha_t), fb = act_fn<ACT_T>(fmaf(v1[c], sc, bias), p.alpha_t);
-          bad |= !(fabsf(fa) <= 65504.0f) | !(fabsf(fb) <= 65504.0f);
-          const uint32_t wa = split16(fa);   // block 2 gb, own channel
-          const uint32_t wb = split16(fb);   // block 2 gb + 1, own channel
-          const uint32_t other = __shfl_xor_sync(0xffffffffu, odd ? wa : wb, 1);
-          const uint32_t first = odd ? other : wa, second = odd ? wb : other;             // channels 2k, 2k + 1 of the stored block
-          *reinterpret_cast<uint32_t*>(frow_a + off0 + c * (kUp * 16)) = __byte_perm(first, second, 0x5410);
-          low[c] = __byte_perm(first, second, 0x7632);
+          const __half2 h = __floats2half2_rn(fa, fb);   // (block 2 gb, block 2 gb + 1), own channel
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(fa - hf.x, fb - hf.y);
+#ifndef FSR_NO_BUILDER_CHECK
+          hmax = __hmax2(hmax, __habs2(h));
+#endif
+          const uint32_t uh = *reinterpret_cast<const uint32_t*>(&h), ul = *reinterpret_cast<const uint32_t*>(&l);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, __byte_perm(uh, ul, sel_send), 1);
+          *reinterpret_cast<uint32_t*>(frow_a + off0 + c * (kUp * 16)) = __byte_perm(uh, other, sel_hi);
+          low[c] = __byte_perm(ul, other, sel_lo);
         }
-        if (bad) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);
+        if (__hisinf(__low2half(hmax)) || __hisinf(__high2half(hmax))) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&f_full[fs_a]);
@@ -421,11 +432,16 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         for (int g = 0; g < kW / 32; ++g) {
           const int px = g * 32 + lane;
           const float* drow = reinterpret_cast<const float*>(smem_dem + as * kDemRow) + px;  // halo index of px - 1
-          const uint32_t h0 = split16(drow[0]), h1 = split16(drow[1]), h2 = split16(drow[2]);
+          const float d0 = drow[0], d1 = drow[1], d2 = drow[2];
+          const __half2 h01 = __floats2half2_rn(d0, d1), h2z = __floats2half2_rn(d2, 0.0f);
+          const float2 f01 = __half22float2(h01), f2z = __half22float2(h2z);
+          const __half2 l01 = __floats2half2_rn(d0 - f01.x, d1 - f01.y), l2z = __floats2half2_rn(d2 - f2z.x, 0.0f);
+          const uint32_t uh01 = *reinterpret_cast<const uint32_t*>(&h01), uh2 = *reinterpret_cast<const uint32_t*>(&h2z);
+          const uint32_t ul01 = *reinterpret_cast<const uint32_t*>(&l01), ul2 = *reinterpret_cast<const uint32_t*>(&l2z);
           uint4 v;
-          v.x = __byte_perm(h0, h1, 0x5410);  // hi(-1), hi(0)
-          v.y = __byte_perm(h2, h0, 0x7610);  // hi(+1), lo(-1)
-          v.z = __byte_perm(h1, h2, 0x7632);  // lo(0), lo(+1)
+          v.x = uh01;                              // hi(-1), hi(0)
+          v.y = __byte_perm(uh2, ul01, 0x5410);    // hi(+1), lo(-1)
+          v.z = __byte_perm(ul01, ul2, 0x5432);    // lo(0), lo(+1)
           v.w = 0u;
           reinterpret_cast<uint4*>(smem_a2 + as * kA2Row)[px] = v;
         }
@@ -576,7 +592,9 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
           }
           const float out = (o0 + o1) + (o2 + o3);
           const size_t off = ((size_t)it.img * p.H + (it.y0 + j)) * kW + s * 128 + m;
+#ifndef FSR_NO_EPI_CHECK
           if (!(fabsf(out) <= 3.0e38f)) atomicOr(p.flags, FSR_FLAG_PRED_NONFINITE);  // Inf / NaN: never in a healthy run
+#endif
           if (p.pred_norm) p.pred_norm[off] = out;
           const float yn = fminf(fmaxf(out, 0.0f), 1.0f);
           p.pred_m[off] = fminf(fmaxf(expm1f(__fmul_rn(yn, p.denom)), 0.0f), p.max_depth);
