@@ -15,8 +15,10 @@
 //   * the DEM column is two K steps: [dem_hi(-1,0,+1), dem_lo(-1,0,+1)] x [Wd_hi, Wd_hi] and [dem_hi(-1,0,+1)] x [Wd_lo];
 //   * DEM rows have their own 2-deep ring (prefetch -> operand builder -> head issuers).
 //
-// Warps: 0 loader (TMA) | 1, 21 head MMA issuers (strips 0-1 / 2-3) | 2 DEM prefetch | 3 DEM operand builder |
-// 4-11 epilogue | 12-19 F builders | 20 convT MMA issuer.  All hand-offs are mbarriers.
+// Warps: 0 loader (TMA) | 1, 25 head MMA issuers (strips 0-1 / 2-3) | 2 DEM prefetch | 3 DEM operand builder |
+// 4-7 epilogue | 8-23 F builders (2 block pairs x 4 TMEM lane quarters x 2 halves of the row's cells) | 24 convT MMA issuer.
+// All hand-offs are mbarriers.  The F builders are what the row time follows (measured), hence sixteen of them with 16 cells
+// each; the epilogue has three MMAs' worth of time per product and needs only one warpgroup.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -53,7 +55,9 @@ constexpr int kA2Row = kW * 16;                   // DEM operand of one row: [51
 constexpr int kA2Stages = 2;
 constexpr int kDemRow = 2176;                     // fp32 DEM halo row (514 floats), 128-byte aligned
 constexpr int kZero = 2048;
-constexpr int kThreads = 22 * 32;
+constexpr int kThreads = 26 * 32;
+constexpr int kBuilders = 16;                     // F-builder warps (8 .. 23)
+constexpr int kCellsPerBuilder = kCells / 2;
 constexpr int kSmemBytes = kHwBytes + kWtStages * kWtStage + kFStages * kFRow + kA2Stages * (kA2Row + kDemRow) + kZero + 1024;
 constexpr int kDcol = kStrips * 3 * kC;           // first TMEM column of the convT accumulator (384)
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -157,8 +161,8 @@ __device__ __forceinline__ float act_fn(float v, float alpha) {
 }
 
 template <int ACT, int ACT_T>
-__global__ void __launch_bounds__(kThreads, 1)  // 80 registers: the register file is split per SM sub-partition (16 K each), which
-                                                // holds 6 of the 22 warps: 6 x 32 x 88 would not fit
+__global__ void __launch_bounds__(kThreads, 1)  // 72 registers: the register file is split per SM sub-partition (16 K each), which
+                                                // holds 7 of the 26 warps
 fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ X3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem_hw = smem_raw;                                  // head weights
@@ -193,9 +197,9 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         mbar_init(&wt_empty[i], 1);
       }
       mbar_init(d_full, 1);
-      mbar_init(d_empty, 8);
+      mbar_init(d_empty, kBuilders);
       for (int i = 0; i < kFStages; ++i) {
-        mbar_init(&f_full[i], 8);
+        mbar_init(&f_full[i], kBuilders);
         mbar_init(&f_empty[i], 2);
       }
       for (int i = 0; i < kA2Stages; ++i) {
@@ -255,7 +259,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         }
       }
     }
-  } else if (warp == 20) {
+  } else if (warp == 24) {
     // ===================== convT MMA issuer: D_t[(kx, co), cell] for one row, three MMAs per (block, K half) ==========
     const uint32_t idesc = idesc_16(128, kCells, 1);
     const uint32_t wt0 = smem_u32(smem_wt);
@@ -287,10 +291,12 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         dph ^= 1;
       }
     }
-  } else if (warp >= 12 && warp < 20) {
+  } else if (warp >= 8 && warp < 8 + kBuilders) {
     // ===================== F builders: TMEM D_t -> scale, + bias, activation, split -> hi stage, then lo stage =========
-    // warp group gb handles blocks 2 gb and 2 gb + 1 (kx = 4 b + q); lane == co, TMEM lane quarter q == kx within the block
-    const int gb = (warp - 12) >> 2;
+    // warp (gb, q, ch) handles blocks 2 gb and 2 gb + 1 (kx = 4 b + q) for cells [16 ch, 16 ch + 16); lane == co, TMEM lane
+    // quarter q == kx within the block
+    const int gb = ((warp - 8) >> 2) & 1;
+    const int ch = (warp - 8) >> 3;
     const int q = warp & 3;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + kDcol;
     const float bias = p.bias_t[lane];
@@ -311,12 +317,12 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         if (y < 0 || y >= p.H) {
           // zero padding row of the head convolution (both parts)
           wait_relaxed(&f_empty[fs_a], ph_a, p.wait_build_ns);
-          for (int k = (warp - 12) * 32 + lane; k < kFRow / 16; k += 256) reinterpret_cast<uint4*>(frow_a)[k] = make_uint4(0, 0, 0, 0);
+          for (int k = (warp - 8) * 32 + lane; k < kFRow / 16; k += kBuilders * 32) reinterpret_cast<uint4*>(frow_a)[k] = make_uint4(0, 0, 0, 0);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&f_full[fs_a]);
           wait_relaxed(&f_empty[fs_b], ph_b, p.wait_build_ns);
-          for (int k = (warp - 12) * 32 + lane; k < kFRow / 16; k += 256) reinterpret_cast<uint4*>(frow_b)[k] = make_uint4(0, 0, 0, 0);
+          for (int k = (warp - 8) * 32 + lane; k < kFRow / 16; k += kBuilders * 32) reinterpret_cast<uint4*>(frow_b)[k] = make_uint4(0, 0, 0, 0);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&f_full[fs_b]);
@@ -325,9 +331,9 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         wait_relaxed(d_full, dph, p.wait_build_ns);
         dph ^= 1;
         tc_fence_after();
-        float v0[32], v1[32];
-        tmem_ld32(lane_addr + (2 * gb) * kCells, v0);
-        tmem_ld32(lane_addr + (2 * gb + 1) * kCells, v1);
+        float v0[kCellsPerBuilder], v1[kCellsPerBuilder];
+        tmem_ld16(lane_addr + (2 * gb) * kCells + ch * kCellsPerBuilder, v0);
+        tmem_ld16(lane_addr + (2 * gb + 1) * kCells + ch * kCellsPerBuilder, v1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -337,19 +343,19 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         // travel together through the shuffle
         const bool odd = lane & 1;
         const uint32_t off0 = (uint32_t)(lane >> 3) * kFPlane + (uint32_t)((lane & 7) >> 1) * 4 +
-                              (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q) * 16;
+                              (uint32_t)(1 + 4 * (2 * gb + (odd ? 1 : 0)) + q + ch * kCellsPerBuilder * kUp) * 16;
         // The kernel's time follows the builders' instruction count (measured: +2 instructions per cell = +9 %), so a cell is
         // ~16 instructions: PACKED conversions (one F2FP for the two blocks' values; scalar F2F runs on a quarter-rate pipe), one
         // shuffle carrying the (hi, lo) the neighbouring lane needs, byte permutes instead of shifts and selects.  The even lane
         // stores the channel pair (2k, 2k + 1) of block 2 gb, the odd lane that of block 2 gb + 1.
         const uint32_t sel_send = odd ? 0x5410u : 0x7632u;
         const uint32_t sel_hi = odd ? 0x3254u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7610u;
-        uint32_t low[kCells];
+        uint32_t low[kCellsPerBuilder];
         __half2 hmax = __floats2half2_rn(0.0f, 0.0f);  // largest |hi| stored: Inf = a feature value that does not fit fp16 (see
                                                        // flag_unstorable in k_tc_conv.cu)
         wait_relaxed(&f_empty[fs_a], ph_a, p.wait_build_ns);
 #pragma unroll
-        for (int c = 0; c < kCells; ++c) {
+        for (int c = 0; c < kCellsPerBuilder; ++c) {
           const float fa = act_fn<ACT_T>(fmaf(v0[c], sc, bias), p.alpha_t), fb = act_fn<ACT_T>(fmaf(v1[c], sc, bias), p.alpha_t);
           const __half2 h = __floats2half2_rn(fa, fb);   // (block 2 gb, block 2 gb + 1), own channel
           const float2 hf = __half22float2(h);
@@ -368,7 +374,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         if (lane == 0) mbar_arrive(&f_full[fs_a]);
         wait_relaxed(&f_empty[fs_b], ph_b, p.wait_build_ns);
 #pragma unroll
-        for (int c = 0; c < kCells; ++c) *reinterpret_cast<uint32_t*>(frow_b + off0 + c * (kUp * 16)) = low[c];
+        for (int c = 0; c < kCellsPerBuilder; ++c) *reinterpret_cast<uint32_t*>(frow_b + off0 + c * (kUp * 16)) = low[c];
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&f_full[fs_b]);
@@ -451,8 +457,8 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         if (++as == kA2Stages) { as = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1 || warp == 21) {
-    // ===================== head MMA issuers (warp 1: strips 0-1, warp 21: strips 2-3) ====================================
+  } else if (warp == 1 || warp == 25) {
+    // ===================== head MMA issuers (warp 1: strips 0-1, warp 25: strips 2-3) ====================================
     const uint32_t idesc0 = idesc_16(128, 0, 1);  // + (N >> 3) << 17
     const int s_begin = warp == 1 ? 0 : 2;
     const uint32_t idesc96 = idesc0 + (3u << 19), idesc32 = idesc0 + (1u << 19);
@@ -558,8 +564,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue (warps 4-11): strips alternate between the two warpgroups ================
-    const int grp = (warp - 4) >> 2;
+    // ===================== epilogue (warps 4-7): one warpgroup drains all four strips ================
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -570,7 +575,7 @@ fused_hr_x3_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
         const int r = go + j;
         const int slot = r % 3;
         const uint32_t par = (r / 3) & 1;
-        for (int s = grp; s < kStrips; s += 2) {
+        for (int s = 0; s < kStrips; ++s) {
           wait_relaxed(&slot_full[s * 3 + slot], par, p.wait_epi_ns);
           tc_fence_after();
           const uint32_t taddr = lane_addr + s * (3 * kC) + slot * kC;

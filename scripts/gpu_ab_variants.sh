@@ -1,4 +1,4 @@
-for v in default nob default2; do
+for v in default b8 default2; do
   if [ $v = default ] || [ $v = default2 ]; then unset FLOODSR_B200_LIB; else export FLOODSR_B200_LIB=$PWD/build/variants/lib_$v.so; fi
   timeout 300 python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/abv_$v.json 2>/dev/null
   python -c "
