@@ -38,6 +38,8 @@ Engine::Engine(const void* plan, size_t plan_bytes, const float* weights, size_t
   FSR_REQUIRE(precision == FSR_PREC_FP32 || precision == FSR_PREC_FP16 || precision == FSR_PREC_FP32_SIMT, "unknown precision mode");
   if (precision == FSR_PREC_FP32) band_tiles_ = 255;  // compute-bound mode: larger bands (measured e2e 24.8 -> 23.6 ms at 935 windows)
   if (const char* e = getenv("FSR_BAND_TILES")) band_tiles_ = std::max(1, atoi(e));
+  if (precision == FSR_PREC_FP16) group_tiles_ = 170;  // copy-bound mode: a group waits for its last row, keep groups short
+  if (const char* e = getenv("FSR_GROUP_TILES")) group_tiles_ = std::max(1, atoi(e));
   no_lazy_dem_ = getenv("FSR_NO_LAZY_DEM") != nullptr;
 
   const size_t hr_px = (size_t)hdr_.hr_tile * hdr_.hr_tile;
@@ -319,6 +321,49 @@ void Engine::run_tiles_from_grid(const float* d_depth, const float* d_dem, const
   }
 }
 
+void Engine::group_lr(const float* d_depth, const float* d_dem, const TileGrid& grid, int n, const fsr_tile_params& p, float* d_stats,
+                      cudaStream_t s) {
+  FSR_REQUIRE(phases_ok(), "the two-phase path needs the fused tensor-core kernels");
+  FSR_REQUIRE(n > 0 && n <= chunk_tiles_, "a group is at most one chunk of windows");
+  group_n_ = 0;
+  ensure_arena(n);
+  const bool lazy = p.normalize_inputs && !no_lazy_dem_ && lazy_dem_ok();  // see run_tiles_from_grid
+  {
+    ProfScope scope(prof, PROF_PROLOGUE, s);
+    launch_tile_normalize(d_dem, d_depth, grid, 0, n, hdr_.hr_tile, hdr_.lr_tile, hdr_.scale, p, lazy ? nullptr : d_dem_norm_.as<float>(),
+                          d_depth_norm_.as<float>(), d_stats, d_dem_lr_.as<float>(), d_flags(), s);
+  }
+  dem_lr_pre_ = p.normalize_inputs ? d_dem_lr_.as<float>() : nullptr;
+  dem_src_ = DemSource{};
+  if (lazy) {
+    dem_src_.on = 1;
+    dem_src_.ras = d_dem;
+    dem_src_.origins = grid.origins;
+    dem_src_.stats = d_stats;
+    dem_src_.H = grid.H;
+    dem_src_.W = grid.W;
+    dem_src_.has_nodata = p.has_dem_nodata;
+    dem_src_.nodata = p.dem_nodata;
+    dem_src_.nodata_tol = p.dem_nodata_tol;
+  }
+  for (size_t i = 0; i < tensors_.size(); ++i) tbase_[i] = tbuf_[i].as<float>();
+  tbase_[0] = d_depth_norm_.as<float>();
+  tbase_[1] = lazy ? nullptr : d_dem_norm_.as<float>();
+  tbase_[hdr_.out_tensor] = nullptr;
+  skip_op_ = -1;
+  if (dem_lr_pre_ && pooled_op_ >= 0) {
+    tbase_[ops_[pooled_op_].dst] = const_cast<float*>(dem_lr_pre_);
+    skip_op_ = pooled_op_;
+  }
+  tc_run_ops(false, n, 0, nullptr, p.max_depth, p.depth_denom, s);
+  group_n_ = n;
+}
+
+void Engine::group_hr(int sub0, int m, float* d_pred_m, const fsr_tile_params& p, cudaStream_t s) {
+  FSR_REQUIRE(sub0 >= 0 && m > 0 && sub0 + m <= group_n_, "windows outside the resident group");
+  tc_run_fused(m, d_pred_m, p.max_depth, p.depth_denom, s, sub0);
+}
+
 unsigned Engine::fetch_flags(cudaStream_t s) {
   unsigned f = 0;
   FSR_CUDA(cudaMemcpyAsync(&f, d_flags_.p, sizeof(f), cudaMemcpyDeviceToHost, s));
@@ -447,23 +492,14 @@ static void band_rows(const Engine& e, int ty0, int ty1, int& row0, int& n_rows,
   halo_out = ty1 >= ny ? 0 : std::max(std::min(ys[ty1 - 1] + T, H) - row_end, 0);
 }
 
-// d_depth/d_dem hold raster rows starting at band_row0 (HR rows; band_row0 % scale == 0), band_rows_hr of them.
-static void band_run(Engine& e, const float* d_depth, const float* d_dem, int band_row0, int band_rows_hr, int ty0, int ty1,
-                     const fsr_tile_params& p, float* d_halo_out, float* d_stats, cudaStream_t s, DeviceBuf* tiles_buf = nullptr,
-                     const int2* d_origins = nullptr) {
+// Window grid of the window rows [ty0, ty1) over raster rows that start at band_row0 (origins relative to that row).
+static TileGrid band_grid(Engine& e, int band_row0, int band_rows_hr, int ty0, int ty1, const int2* d_origins, cudaStream_t s) {
   const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T;
   FSR_REQUIRE(ty0 >= 0 && ty0 < ty1 && ty1 <= ny, "bad tile-row range");
   FSR_REQUIRE(band_row0 % e.scale() == 0 && band_row0 <= e.win.ys[ty0], "band rows do not cover the band's first window");
   const int need_end = std::min(e.win.ys[ty1 - 1] + T, e.win.H);
   FSR_REQUIRE(band_row0 + band_rows_hr >= need_end, "band rows do not cover the band's last window");
   const int n_tiles = (ty1 - ty0) * nx;
-  DeviceBuf& tiles = tiles_buf ? *tiles_buf : e.d_tiles;
-  tiles.ensure((size_t)n_tiles * T * T * sizeof(float));
-  float* stats = d_stats;
-  if (!stats) {
-    e.d_stats.ensure((size_t)n_tiles * 3 * sizeof(float));
-    stats = e.d_stats.as<float>();
-  }
   TileGrid grid;
   if (d_origins) {
     grid.origins = d_origins;  // uploaded by the caller, relative to band_row0
@@ -488,7 +524,39 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
   grid.Hl = ceil_div(grid.H, e.scale());
   grid.Hl = std::min(grid.Hl, e.win.H / e.scale() - band_row0 / e.scale());
   grid.Wl = e.win.W / e.scale();
-  e.run_tiles_from_grid(d_depth, d_dem, grid, 0, n_tiles, p, tiles.as<float>(), nullptr, stats, s);
+  return grid;
+}
+
+// First phase for a GROUP of bands, window rows [gy0, gy1): a5-a8 and the low-resolution layers of all its windows in one
+// batch (Engine::group_lr).  The bands of the group then call band_run with group_ty0 = gy0.
+static void group_run_lr(Engine& e, const float* d_depth, const float* d_dem, int band_row0, int band_rows_hr, int gy0, int gy1,
+                         const fsr_tile_params& p, float* d_stats, cudaStream_t s, const int2* d_origins = nullptr) {
+  const TileGrid grid = band_grid(e, band_row0, band_rows_hr, gy0, gy1, d_origins, s);
+  e.group_lr(d_depth, d_dem, grid, (gy1 - gy0) * (int)e.win.xs.size(), p, d_stats, s);
+}
+
+// d_depth/d_dem hold raster rows starting at band_row0 (HR rows; band_row0 % scale == 0), band_rows_hr of them.
+// group_ty0 >= 0: the band belongs to the group whose first phase has run (group_run_lr), only the high-resolution kernel and
+// the hand-over sums remain.
+static void band_run(Engine& e, const float* d_depth, const float* d_dem, int band_row0, int band_rows_hr, int ty0, int ty1,
+                     const fsr_tile_params& p, float* d_halo_out, float* d_stats, cudaStream_t s, DeviceBuf* tiles_buf = nullptr,
+                     const int2* d_origins = nullptr, int group_ty0 = -1) {
+  const int nx = (int)e.win.xs.size(), T = e.win.T;
+  const int n_tiles = (ty1 - ty0) * nx;
+  DeviceBuf& tiles = tiles_buf ? *tiles_buf : e.d_tiles;
+  tiles.ensure((size_t)n_tiles * T * T * sizeof(float));
+  if (group_ty0 >= 0) {
+    FSR_REQUIRE(ty0 >= group_ty0 && ty0 < ty1 && ty1 <= (int)e.win.ys.size(), "bad tile-row range");
+    e.group_hr((ty0 - group_ty0) * nx, n_tiles, tiles.as<float>(), p, s);
+  } else {
+    float* stats = d_stats;
+    if (!stats) {
+      e.d_stats.ensure((size_t)n_tiles * 3 * sizeof(float));
+      stats = e.d_stats.as<float>();
+    }
+    const TileGrid grid = band_grid(e, band_row0, band_rows_hr, ty0, ty1, d_origins, s);
+    e.run_tiles_from_grid(d_depth, d_dem, grid, 0, n_tiles, p, tiles.as<float>(), nullptr, stats, s);
+  }
   int row0, n_rows, halo_out;
   band_rows(e, ty0, ty1, row0, n_rows, halo_out);
   e.band = BandState{ty0, ty1, row0, n_rows, halo_out, p.max_depth};
@@ -503,12 +571,13 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
 // kernels efficient, small enough to overlap copies; the first band is a single window row so that the pipeline fills fast.
 // A band must own at least the rows it receives partial sums for (three or more window rows covering one coordinate:
 // overlap >= tile / 2 or a forced trailing window close to its predecessor): such a band takes over the following window rows.
-static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1) {
+static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1, bool single_rows = false) {
   const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T, H = e.win.H;
-  // band size: the engine's target, but at least ~4 bands per call so that small rasters still overlap copies and kernels
+  // band size: the engine's target, but at least ~4 bands per call so that small rasters still overlap copies and kernels;
+  // single_rows (two-phase pipeline, where the batched layers run per GROUP of bands): one window row per band
   const int total = (ty1 - ty0) * nx;
   const int target = std::min(e.band_tiles_target(), std::max(64, ceil_div(total, 4)));
-  const int rows_per_band = std::max(1, ceil_div(target, nx));
+  const int rows_per_band = single_rows ? 1 : std::max(1, ceil_div(target, nx));
   std::vector<int> band_ty{ty0};  // band b covers window rows [band_ty[b], band_ty[b + 1])
   if (ty1 - ty0 >= 3 && rows_per_band > 1) band_ty.push_back(ty0 + 1);
   while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
@@ -531,6 +600,38 @@ static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1) {
       break;
   }
   return band_ty;
+}
+
+// Groups of consecutive bands for the two-phase pipeline: group k covers bands [g[k], g[k + 1]).  The first group is the first
+// band alone (the pipeline starts as soon as one window row has arrived), the following groups double in size up to the
+// engine's target: the batched low-resolution layers lose throughput on small batches, while a group cannot start before its
+// last row has been copied in.  Without the two-phase path every band is its own group.
+static std::vector<int> group_plan(const Engine& e, const std::vector<int>& band_ty, bool phases) {
+  const int n_bands = (int)band_ty.size() - 1, nx = (int)e.win.xs.size();
+  std::vector<int> g{0};
+  if (!phases) {
+    for (int b = 1; b <= n_bands; ++b) g.push_back(b);
+    return g;
+  }
+  const int cap = std::min(e.chunk_tiles(), e.group_tiles_target());
+  long long limit = (long long)(band_ty[1] - band_ty[0]) * nx;
+  for (int b = 0; b < n_bands;) {
+    int b1 = b + 1;
+    while (b1 < n_bands && (long long)(band_ty[b1 + 1] - band_ty[b]) * nx <= limit) ++b1;
+    g.push_back(b1);
+    b = b1;
+    limit = std::min<long long>(2 * limit, cap);
+  }
+  return g;
+}
+
+// the two-phase pipeline applies when the fused tensor-core kernels run the high-resolution layers and no band exceeds a chunk
+static bool use_phases(const Engine& e, const fsr_tile_params& p, const std::vector<int>& band_ty) {
+  static const bool off = getenv("FSR_NO_PHASES") != nullptr;
+  if (off || !e.phases_ok() || !p.normalize_inputs) return false;
+  for (size_t b = 0; b + 1 < band_ty.size(); ++b)
+    if ((long long)(band_ty[b + 1] - band_ty[b]) * (long long)e.win.xs.size() > e.chunk_tiles()) return false;
+  return true;
 }
 
 static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s,
@@ -699,7 +800,10 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
   e.d_stats.ensure((size_t)ny * nx * 3 * sizeof(float));
   // (a single-row LAST band was measured slower than letting the last band keep its two rows: small batches run the LR
   // layers at a third of their throughput)
-  const std::vector<int> band_ty = sub_band_plan(e, 0, ny);
+  std::vector<int> band_ty = sub_band_plan(e, 0, ny, true);
+  const bool phases = use_phases(e, *params, band_ty);
+  if (!phases) band_ty = sub_band_plan(e, 0, ny);
+  const std::vector<int> group_b = group_plan(e, band_ty, phases);
   const int n_bands = (int)band_ty.size() - 1;
   e.d_halo[0].ensure((size_t)T * W * sizeof(float));
   e.d_halo[1].ensure((size_t)T * W * sizeof(float));
@@ -737,11 +841,18 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
     FSR_CUDA(cudaEventRecord(ev_in[b], si));
   }
   h_enq_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
-  for (int b = 0; b < n_bands; ++b) {
+  for (int b = 0, g = 0; b < n_bands; ++b) {
     const int ty0 = band_ty[b], ty1 = band_ty[b + 1];
-    FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[b], 0));
+    if (b == group_b[g]) {  // a new group starts: it needs the rows of its last band
+      const int gb1 = group_b[g + 1];
+      FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[gb1 - 1], 0));
+      if (phases)
+        group_run_lr(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), 0, H, ty0, band_ty[gb1], *params,
+                     e.d_stats.as<float>() + (size_t)ty0 * nx * 3, sc_);
+      ++g;
+    }
     band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), 0, H, ty0, ty1, *params, e.d_halo[b & 1].as<float>(),
-             e.d_stats.as<float>() + (size_t)ty0 * nx * 3, sc_);
+             e.d_stats.as<float>() + (size_t)ty0 * nx * 3, sc_, nullptr, nullptr, phases ? band_ty[group_b[g - 1]] : -1);
     const int halo_in = b == 0 ? 0 : e.band_halo_rows[(b - 1) & 1];
     e.band_halo_rows[b & 1] = e.band.halo_out_rows;
     band_finalize(e, b == 0 ? nullptr : e.d_halo[(b - 1) & 1].as<float>(), halo_in, e.d_out.as<float>() + (size_t)e.band.row0 * W, sc_);
@@ -765,8 +876,8 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
     cudaEventElapsedTime(&a, t_start, t_in);
     cudaEventElapsedTime(&b, t_start, t_comp);
     cudaEventElapsedTime(&c, t_start, t_out);
-    fprintf(stderr, "[fsr_run_raster] %d bands: H2D done %.2f ms, kernels done %.2f ms, D2H done %.2f ms | host: inputs queued %.2f, bands queued",
-            n_bands, a, b, c, h_enq_in);
+    fprintf(stderr, "[fsr_run_raster] %d bands in %d groups: H2D done %.2f ms, kernels done %.2f ms, D2H done %.2f ms | host: inputs queued %.2f, bands queued",
+            n_bands, (int)group_b.size() - 1, a, b, c, h_enq_in);
     for (int k = 0; k < n_bands && k < 16; ++k) fprintf(stderr, " %.2f", h_band[k]);
     fprintf(stderr, " ms | per band (H2D done, kernels done):");
     for (int k = 0; k < n_bands; ++k) {
@@ -881,8 +992,12 @@ int fsr_band_host_begin(fsr_engine* eng, const float* depth_lr, const float* dem
     FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, sc_));
     FSR_CUDA(cudaStreamSynchronize(sc_));
   }
-  const std::vector<int> band_ty = sub_band_plan(e, ty0, ty1);
+  std::vector<int> band_ty = sub_band_plan(e, ty0, ty1, true);
+  const bool phases = use_phases(e, *params, band_ty);
+  if (!phases) band_ty = sub_band_plan(e, ty0, ty1);
+  const std::vector<int> group_b = group_plan(e, band_ty, phases);
   const int n_bands = (int)band_ty.size() - 1;
+  if (phases) e.d_stats.ensure((size_t)(ty1 - ty0) * nx * 3 * sizeof(float));
   std::vector<cudaEvent_t> ev_in(n_bands), ev_done(n_bands);
   for (int b = 0; b < n_bands; ++b) {
     FSR_CUDA(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
@@ -907,13 +1022,21 @@ int fsr_band_host_begin(fsr_engine* eng, const float* depth_lr, const float* dem
     FSR_CUDA(cudaEventRecord(ev_in[b], si));
   }
   const bool defer_first = ty0 > 0;  // rows shared with the previous rank: blended in fsr_band_host_end
-  for (int b = 0; b < n_bands; ++b) {
+  for (int b = 0, g = 0; b < n_bands; ++b) {
     const int s0 = band_ty[b], s1 = band_ty[b + 1];
     const bool last = b == n_bands - 1;
-    FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[b], 0));
+    if (b == group_b[g]) {  // a new group starts: it needs the rows of its last band
+      const int gb1 = group_b[g + 1];
+      FSR_CUDA(cudaStreamWaitEvent(sc_, ev_in[gb1 - 1], 0));
+      if (phases)
+        group_run_lr(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), band_row0, band_rows_hr, s0, band_ty[gb1], *params,
+                     e.d_stats.as<float>() + (size_t)(s0 - ty0) * nx * 3, sc_, e.d_tmp_a.as<int2>() + (size_t)(s0 - ty0) * nx);
+      ++g;
+    }
     float* halo_dst = (last && d_halo_out) ? d_halo_out : e.d_halo[b & 1].as<float>();
     band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), band_row0, band_rows_hr, s0, s1, *params, halo_dst, nullptr, sc_,
-             (b == 0 && defer_first) ? &e.d_tiles0 : nullptr, e.d_tmp_a.as<int2>() + (size_t)(s0 - ty0) * nx);
+             (b == 0 && defer_first) ? &e.d_tiles0 : nullptr, e.d_tmp_a.as<int2>() + (size_t)(s0 - ty0) * nx,
+             phases ? band_ty[group_b[g - 1]] : -1);
     const int halo_in = b == 0 ? 0 : e.band_halo_rows[(b - 1) & 1];
     e.band_halo_rows[b & 1] = e.band.halo_out_rows;
     if (b == 0 && defer_first) {

@@ -162,6 +162,17 @@ class Engine {
   void run_tiles_from_grid(const float* d_depth, const float* d_dem, const TileGrid& grid, int tile_base, int n_tiles,
                            const fsr_tile_params& p, float* d_pred_m, float* d_pred_norm, float* d_stats, cudaStream_t s);
 
+  // The same work in two phases, for the copy / compute pipelines: the batched low-resolution layers want many windows per
+  // launch (a band of one window row runs them at a third of their throughput), copies want small bands.  group_lr runs
+  // a5-a8 and the low-resolution layers for a GROUP of windows (<= one chunk); group_hr then runs the fused high-resolution
+  // kernel for windows [sub0, sub0 + m) of that group, so that a band's rows can be blended and copied out while the next
+  // band of the same group is still computing.  Per-window results do not depend on how windows are batched.
+  bool phases_ok() const { return precision_ != FSR_PREC_FP32_SIMT && fused_ct_ >= 0 && pooled_op_ != fused_ct_ && pooled_op_ != fused_hd_; }
+  int chunk_tiles() const { return chunk_tiles_; }
+  void group_lr(const float* d_depth, const float* d_dem, const TileGrid& grid, int n_tiles, const fsr_tile_params& p, float* d_stats,
+                cudaStream_t s);
+  void group_hr(int sub0, int m, float* d_pred_m, const fsr_tile_params& p, cudaStream_t s);
+
   void setup_windows(int H, int W, int method, int overlap, const int* ys, int ny, const int* xs, int nx,
                      const float* ramp, cudaStream_t s);
   BlendGeom blend_geom() const;
@@ -187,6 +198,7 @@ class Engine {
     FSR_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
   }
   int band_tiles_target() const { return band_tiles_; }
+  int group_tiles_target() const { return group_tiles_; }
   // fsr_band_host_begin/_end: the sub-band sharing rows with the previous rank is blended last
   DeviceBuf d_tiles0;
   BandState band0;
@@ -206,7 +218,8 @@ class Engine {
   void tc_run_one(int op, int n, int sub_start, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int head_sms);
   void tc_run_hr_phase(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
   void tc_prepare_fused(const float* host_weights);
-  void tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  void tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int sub0 = 0);
+  int group_n_ = 0;                     // windows of the group whose low-resolution result is resident (group_lr)
   void run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
   bool hr_simt_ = false;                // the high-resolution layers run on the fp32 FMA kernels (shapes the tcgen05 kernels do not cover)
   int parts_ = 1;                       // 2: split fp16 (hi, lo) tensors and weights, three MMAs per product (FSR_PREC_FP32)
@@ -236,6 +249,7 @@ class Engine {
   int hr_sub_ = 4;               // tiles per HR sub-chunk (tensor-core modes: 64; env FSR_HR_SUB overrides)
   int chunk_tiles_ = 64;
   int band_tiles_ = 170;         // windows per band of the fsr_run_raster copy/compute pipeline (env FSR_BAND_TILES)
+  int group_tiles_ = 340;        // two-phase pipeline: largest group of windows whose low-resolution layers run in one batch (env FSR_GROUP_TILES)
   DeviceBuf d_weights_, d_flags_, d_headmid_;
   std::vector<DeviceBuf> tbuf_;
   std::vector<float*> tbase_;    // per-forward tensor base pointers (inputs/outputs alias caller buffers)

@@ -344,29 +344,39 @@ void Engine::tc_prepare_fused(const float* w) {
   fused_hd_ = hr_ops[1];
 }
 
-void Engine::tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s) {
+// Windows [sub0, sub0 + n) of the batch whose low-resolution result (and normalised inputs) are resident.
+void Engine::tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int sub0) {
   const fsr_op& ct = ops_[fused_ct_];
   const fsr_op& hd = ops_[fused_hd_];
   const TcOp& th = tc_ops_[fused_hd_];
   const auto& tf = tensors_[ct.dst];
+  const auto& tl = tensors_[ct.src0];
   const int half = 1;
-  float* pn = tbase_[hd.dst];  // may be nullptr when the caller does not want the normalised prediction
+  const size_t hr_px = (size_t)tf.h * tf.w;
+  float* pn = tbase_[hd.dst] ? tbase_[hd.dst] + (size_t)sub0 * hr_px : nullptr;  // nullptr: the caller does not want the normalised prediction
   float* pm = d_pred_m;
   if (!pm) {
-    d_tmp_b.ensure((size_t)n * tf.h * tf.w * sizeof(float));
+    d_tmp_b.ensure((size_t)n * hr_px * sizeof(float));
     pm = d_tmp_b.as<float>();
+  }
+  // image sub0 of the CP8 tensor L (planes are cap_tiles_ images apart, which the tensor map keeps)
+  const __nv_bfloat16* lr = reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]) + (size_t)sub0 * tl.h * tl.w * 8;
+  const float* dem = tbase_[1] ? tbase_[1] + (size_t)sub0 * hr_px : nullptr;
+  DemSource src = dem_src_;
+  if (src.on) {
+    src.origins += sub0;
+    src.stats += (size_t)sub0 * 3;
   }
   ProfScope scope(prof, PROF_HEAD, s);
   if (parts_ == 2) {
-    launch_fused_x3(reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]), tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(),
-                    fused_bias_t_.data(), fused_scale_t_inv_, ct.act, ct.alpha, fused_hw_.as<__nv_bfloat16>(), fused_bias_h_.data(),
-                    fused_scale_h_inv_, th.h_w2.data(), &th.h_b2, hd.act, hd.alpha, tbase_[1], dem_src_, pm, pn, n, tf.h, max_depth, denom,
-                    n_sms_, d_flags(), s);
+    launch_fused_x3(lr, tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(), fused_bias_t_.data(), fused_scale_t_inv_, ct.act, ct.alpha,
+                    fused_hw_.as<__nv_bfloat16>(), fused_bias_h_.data(), fused_scale_h_inv_, th.h_w2.data(), &th.h_b2, hd.act, hd.alpha, dem,
+                    src, pm, pn, n, tf.h, max_depth, denom, n_sms_, d_flags(), s);
     return;
   }
-  launch_fused_hr_tc(reinterpret_cast<const __nv_bfloat16*>(tbase_[ct.src0]), tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(),
-                     fused_bias_t_.data(), ct.act, ct.alpha, fused_hw_.as<__nv_bfloat16>(), th.h_w2.data(), &th.h_b2, hd.act, hd.alpha,
-                     tbase_[1], dem_src_, pm, pn, n, tf.h, max_depth, denom, half, n_sms_, d_flags(), s);
+  launch_fused_hr_tc(lr, tc_plane(ct.src0), fused_wt_.as<__nv_bfloat16>(), fused_bias_t_.data(), ct.act, ct.alpha,
+                     fused_hw_.as<__nv_bfloat16>(), th.h_w2.data(), &th.h_b2, hd.act, hd.alpha, dem, src, pm, pn, n, tf.h, max_depth, denom,
+                     half, n_sms_, d_flags(), s);
 }
 
 void Engine::tc_ensure_arena(int cap) {
