@@ -627,15 +627,15 @@ static std::vector<int> group_plan(const Engine& e, const std::vector<int>& band
 
 // the two-phase pipeline applies when the fused tensor-core kernels run the high-resolution layers and no band exceeds a chunk
 static bool use_phases(const Engine& e, const fsr_tile_params& p, const std::vector<int>& band_ty) {
-  static const bool off = getenv("FSR_NO_PHASES") != nullptr;
-  if (off || !e.phases_ok() || !p.normalize_inputs) return false;
+  if (getenv("FSR_NO_PHASES") || !e.phases_ok() || !p.normalize_inputs) return false;  // (read per call: the tests switch it)
   for (size_t b = 0; b + 1 < band_ty.size(); ++b)
     if ((long long)(band_ty[b + 1] - band_ty[b]) * (long long)e.win.xs.size() > e.chunk_tiles()) return false;
   return true;
 }
 
 static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, float* d_out_rows, cudaStream_t s,
-                          const DeviceBuf* tiles_buf = nullptr, const BandState* st = nullptr, int row_begin = 0, int row_end = -1) {
+                          const DeviceBuf* tiles_buf = nullptr, const BandState* st = nullptr, int row_begin = 0, int row_end = -1,
+                          int x0 = 0, int x1 = -1) {
   BlendGeom g = e.blend_geom();
   const BandState& b = st ? *st : e.band;
   const DeviceBuf& tiles = tiles_buf ? *tiles_buf : e.d_tiles;
@@ -646,7 +646,54 @@ static void band_finalize(Engine& e, const float* d_halo_in, int halo_rows_in, f
               "band owns fewer rows than the incoming halo covers: merge window rows when planning bands (dist.chain_safe_bands)");
   ProfScope scope(e.prof, PROF_BLEND, s);
   launch_blend(tiles.as<float>(), b.ty0, b.ty1, g, b.row0 + row_begin, row_end - row_begin, first ? d_halo_in : nullptr,
-               first ? halo_rows_in : 0, true, b.max_depth, d_out_rows + (size_t)row_begin * g.W, s);
+               first ? halo_rows_in : 0, true, b.max_depth, d_out_rows + (size_t)row_begin * g.W, s, x0, x1);
+}
+
+// The LAST band of a two-phase pipeline in column parts: nothing can overlap what follows the last kernel, so the band's
+// window row is cut into `parts` runs of windows; each run's high-resolution kernel is followed by the blend of the columns it
+// completes (pixels left of window k's origin are covered by windows < k only) and their D2H copy, which then runs next to
+// the following run's kernel.  Same tiles, same per-pixel sums: bit-identical to the band in one piece.
+// d_out_rows / h_out_rows: the band's first owned row on the device / in the caller's (host) raster, both W floats per row.
+static void band_run_tail(Engine& e, int ty0, int group_ty0, const fsr_tile_params& p, const float* d_halo_in, int halo_rows_in,
+                          float* d_halo_out, float* d_out_base, float* h_out_base, int rank_row0, int parts, cudaStream_t sc,
+                          cudaStream_t so) {
+  const int nx = (int)e.win.xs.size(), T = e.win.T, W = e.win.W;
+  e.d_tiles.ensure((size_t)nx * T * T * sizeof(float));
+  int row0, n_rows, halo_out;
+  band_rows(e, ty0, ty0 + 1, row0, n_rows, halo_out);
+  e.band = BandState{ty0, ty0 + 1, row0, n_rows, halo_out, p.max_depth};
+  float* d_rows = d_out_base + (size_t)(row0 - rank_row0) * W;
+  float* h_rows = h_out_base + (size_t)(row0 - rank_row0) * W;
+  for (int part = 0; part < parts; ++part) {
+    const int k0 = nx * part / parts, k1 = nx * (part + 1) / parts;
+    if (k1 <= k0) continue;
+    e.group_hr((ty0 - group_ty0) * nx + k0, k1 - k0, e.d_tiles.as<float>() + (size_t)k0 * T * T, p, sc);
+    const int x0 = part == 0 ? 0 : e.win.xs[k0], x1 = part == parts - 1 ? W : std::min(e.win.xs[k1], W);
+    if (n_rows <= 0 || x1 <= x0) continue;
+    band_finalize(e, d_halo_in, halo_rows_in, d_rows, sc, nullptr, nullptr, 0, -1, x0, x1);
+    cudaEvent_t ev;
+    FSR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    FSR_CUDA(cudaEventRecord(ev, sc));
+    FSR_CUDA(cudaStreamWaitEvent(so, ev, 0));
+    FSR_CUDA(cudaEventDestroy(ev));  // released once the recorded work has completed
+    FSR_CUDA(cudaMemcpy2DAsync(h_rows + x0, (size_t)W * sizeof(float), d_rows + x0, (size_t)W * sizeof(float),
+                               (size_t)(x1 - x0) * sizeof(float), (size_t)n_rows, cudaMemcpyDeviceToHost, so));
+  }
+  if (halo_out > 0 && d_halo_out) {
+    BlendGeom g = e.blend_geom();
+    ProfScope scope(e.prof, PROF_BLEND, sc);
+    launch_blend(e.d_tiles.as<float>(), ty0, ty0 + 1, g, row0 + n_rows, halo_out, nullptr, 0, false, p.max_depth, d_halo_out, sc);
+  }
+}
+
+// column parts of the last band (env FSR_TAIL_PARTS; 1 = off): needs the two-phase path, a band of one window row and window
+// origins the vector blend accepts
+static int tail_parts(const Engine& e, bool phases, int ty0, int ty1) {
+  int parts = 4;
+  if (const char* v = getenv("FSR_TAIL_PARTS")) parts = std::max(1, atoi(v));
+  const int nx = (int)e.win.xs.size();
+  if (!phases || ty1 - ty0 != 1 || !e.win.vec_ok || e.win.W % 4 != 0) return 1;
+  return std::max(1, std::min(parts, nx / 8));
 }
 
 }  // namespace fsr
@@ -851,6 +898,14 @@ int fsr_run_raster(fsr_engine* eng, const float* depth_lr, const float* dem_hr, 
                      e.d_stats.as<float>() + (size_t)ty0 * nx * 3, sc_);
       ++g;
     }
+    const int n_tail = (b == n_bands - 1 && b > 0) ? tail_parts(e, phases, ty0, ty1) : 1;
+    if (n_tail > 1) {
+      band_run_tail(e, ty0, band_ty[group_b[g - 1]], *params, e.d_halo[(b - 1) & 1].as<float>(), e.band_halo_rows[(b - 1) & 1], nullptr,
+                    e.d_out.as<float>(), out_sr, 0, n_tail, sc_, so);
+      FSR_CUDA(cudaEventRecord(ev_done[b], sc_));
+      if (b < 16) h_band[b] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+      continue;
+    }
     band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), 0, H, ty0, ty1, *params, e.d_halo[b & 1].as<float>(),
              e.d_stats.as<float>() + (size_t)ty0 * nx * 3, sc_, nullptr, nullptr, phases ? band_ty[group_b[g - 1]] : -1);
     const int halo_in = b == 0 ? 0 : e.band_halo_rows[(b - 1) & 1];
@@ -1034,6 +1089,13 @@ int fsr_band_host_begin(fsr_engine* eng, const float* depth_lr, const float* dem
       ++g;
     }
     float* halo_dst = (last && d_halo_out) ? d_halo_out : e.d_halo[b & 1].as<float>();
+    const int n_tail = (last && b > 0) ? tail_parts(e, phases, s0, s1) : 1;
+    if (n_tail > 1) {
+      band_run_tail(e, s0, band_ty[group_b[g - 1]], *params, e.d_halo[(b - 1) & 1].as<float>(), e.band_halo_rows[(b - 1) & 1], halo_dst,
+                    e.d_out.as<float>(), out_rows, rank_row0, n_tail, sc_, so);
+      e.band_halo_rows[b & 1] = e.band.halo_out_rows;
+      continue;
+    }
     band_run(e, e.d_in_depth.as<float>(), e.d_in_dem.as<float>(), band_row0, band_rows_hr, s0, s1, *params, halo_dst, nullptr, sc_,
              (b == 0 && defer_first) ? &e.d_tiles0 : nullptr, e.d_tmp_a.as<int2>() + (size_t)(s0 - ty0) * nx,
              phases ? band_ty[group_b[g - 1]] : -1);

@@ -98,7 +98,7 @@ void launch_head_1x1_fp32(const float* feat, const float* w2, const float* b2, f
                           cudaStream_t s);
 void launch_invert_depth(const float* pred_norm, float* pred_m, size_t n, float max_depth, float denom, cudaStream_t s);
 void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, int row0, int n_rows, const float* d_init,
-                  int init_rows, bool finalize, float max_depth, float* d_out, cudaStream_t s);
+                  int init_rows, bool finalize, float max_depth, float* d_out, cudaStream_t s, int x0 = 0, int x1 = -1);
 
 void launch_resample_bilinear(const float* d_src, int sh, int sw, float* d_dst, int dh, int dw, const fsr_resample_params& p,
                               cudaStream_t s);

@@ -26,10 +26,10 @@ __device__ __forceinline__ float edge_weight(const float* __restrict__ ramp, int
 template <int VEC>
 __global__ void __launch_bounds__(256)
 blend_kernel(const float* __restrict__ tiles, int ty0, int ty1, BlendGeom g, int row0, int n_rows,
-             const float* __restrict__ init, int init_rows, int finalize, float max_depth, float* __restrict__ out) {
-  const int xv = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+             const float* __restrict__ init, int init_rows, int finalize, float max_depth, float* __restrict__ out, int x0, int x1) {
+  const int xv = x0 + (blockIdx.x * blockDim.x + threadIdx.x) * VEC;  // columns [x0, x1) of the raster
   const int ry = blockIdx.y;  // row within [0, n_rows)
-  if (xv >= g.W || ry >= n_rows) return;
+  if (xv >= x1 || ry >= n_rows) return;
   const int y = row0 + ry;
   const int yf = g.y_first[y], yc = g.y_count[y];
   const int xf = g.x_first[xv], xc = g.x_count[xv];
@@ -94,9 +94,9 @@ blend_kernel(const float* __restrict__ tiles, int ty0, int ty1, BlendGeom g, int
 template <int R>
 __global__ void __launch_bounds__(256)
 blend_fast_kernel(const float* __restrict__ tiles, int ty0, int ty1, BlendGeom g, int row0, int n_rows,
-                  const float* __restrict__ init, int init_rows, int finalize, float max_depth, float* __restrict__ out) {
-  const int xv = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (xv >= g.W) return;
+                  const float* __restrict__ init, int init_rows, int finalize, float max_depth, float* __restrict__ out, int x0, int x1) {
+  const int xv = x0 + (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // columns [x0, x1) of the raster
+  if (xv >= x1) return;
   const size_t tile_px = (size_t)g.T * g.T;
   // column side
   const int xf = g.x_first[xv], xc = g.x_count[xv];
@@ -180,10 +180,13 @@ blend_fast_kernel(const float* __restrict__ tiles, int ty0, int ty1, BlendGeom g
 }  // namespace
 
 void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, int row0, int n_rows, const float* d_init,
-                  int init_rows, bool finalize, float max_depth, float* d_out, cudaStream_t s) {
-  if (n_rows <= 0) return;
-  const bool vec = g.vec_ok && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0) &&
+                  int init_rows, bool finalize, float max_depth, float* d_out, cudaStream_t s, int x0, int x1) {
+  if (x1 < 0) x1 = g.W;  // columns [x0, x1) of every row (d_out / d_init still point at column 0)
+  if (n_rows <= 0 || x1 <= x0) return;
+  FSR_REQUIRE(x0 >= 0 && x1 <= g.W, "blend columns outside the raster");
+  const bool vec = g.vec_ok && (g.W % 4 == 0) && x0 % 4 == 0 && x1 % 4 == 0 && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0) &&
                    (!d_init || (reinterpret_cast<uintptr_t>(d_init) & 15u) == 0);
+  const int wx = x1 - x0;
   // gridDim.y is limited to 65535 rows per launch
   for (int r0 = 0; r0 < n_rows; r0 += 65535) {
     const int nr = n_rows - r0 < 65535 ? n_rows - r0 : 65535;
@@ -194,17 +197,17 @@ void launch_blend(const float* d_tiles, int ty0, int ty1, const BlendGeom& g, in
       constexpr int R = 2;
       // ~32 blocks per SM, each walking down the rows (measured on B200: 4 -> 0.50 ms, 8 -> 0.39, 32 -> 0.37, one block per
       // row pair -> 0.43); env FSR_BLEND_BLOCKS overrides
-      const int gx = ceil_div(g.W / 4, 256);
+      const int gx = ceil_div(wx / 4, 256);
       static const int per_sm = getenv("FSR_BLEND_BLOCKS") ? atoi(getenv("FSR_BLEND_BLOCKS")) : 32;
       const int gy = std::min(ceil_div(nr, R), std::max(1, (current_sm_count() * per_sm) / gx));
       dim3 grid((unsigned)gx, (unsigned)gy);
-      blend_fast_kernel<R><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp);
+      blend_fast_kernel<R><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp, x0, x1);
     } else if (vec) {
-      dim3 grid((unsigned)ceil_div(g.W / 4, 256), (unsigned)nr);
-      blend_kernel<4><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp);
+      dim3 grid((unsigned)ceil_div(wx / 4, 256), (unsigned)nr);
+      blend_kernel<4><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp, x0, x1);
     } else {
-      dim3 grid((unsigned)ceil_div(g.W, 256), (unsigned)nr);
-      blend_kernel<1><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp);
+      dim3 grid((unsigned)ceil_div(wx, 256), (unsigned)nr);
+      blend_kernel<1><<<grid, 256, 0, s>>>(d_tiles, ty0, ty1, g, row0 + r0, nr, init, irows, finalize ? 1 : 0, max_depth, outp, x0, x1);
     }
     FSR_LAUNCH_CHECK();
   }

@@ -506,6 +506,54 @@ def test_large_overlaps_three_window_rows_per_coordinate(h1_model_fp, oracle_eng
     tiles_engine.close()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_two_phase_pipeline_is_bit_identical_to_band_pipeline(h1_model_fp, monkeypatch, precision):
+    """fsr_run_raster runs the low-resolution layers per GROUP of window rows and the fused high-resolution kernel per window
+    row (two-phase pipeline); FSR_NO_PHASES=1 runs every band in one piece.  Per-window results do not depend on how the
+    windows are batched, so the two mosaics, and the mosaics of other group sizes, are the same bits (7 window rows: groups
+    of 1, 2, 4 rows by default)."""
+    from floodsr_b200.engine import EngineB200
+
+    depth, dem = synth_raster(2816, 1280, seed=77)
+    eng = EngineB200(h1_model_fp, precision=precision)
+    got, n, summary = eng.run_raster(depth, dem)
+    monkeypatch.setenv("FSR_NO_PHASES", "1")
+    want, n_ref, summary_ref = eng.run_raster(depth, dem)
+    monkeypatch.delenv("FSR_NO_PHASES")
+    eng.close()
+    assert n == n_ref and n >= 21 and summary == summary_ref
+    assert np.array_equal(got, want)
+    monkeypatch.setenv("FSR_GROUP_TILES", "8")  # two window rows per group at most
+    small = EngineB200(h1_model_fp, precision=precision)
+    monkeypatch.delenv("FSR_GROUP_TILES")
+    got_small, _, _ = small.run_raster(depth, dem, window_method="hard", overlap_lr=0)
+    monkeypatch.setenv("FSR_NO_PHASES", "1")
+    want_small, _, _ = small.run_raster(depth, dem, window_method="hard", overlap_lr=0)
+    small.close()
+    assert np.array_equal(got_small, want_small)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_last_band_in_column_parts_is_bit_identical(h1_model_fp, monkeypatch, precision):
+    """The last band of the two-phase pipeline runs in column parts (kernel of part k+1 next to the D2H copy of part k): 34
+    window columns give 4 parts.  Same bits as the band pipeline, feather and hard windows."""
+    from floodsr_b200.engine import EngineB200
+
+    depth, dem = synth_raster(1280, 13184, seed=5)
+    eng = EngineB200(h1_model_fp, precision=precision)
+    for kw in ({}, {"window_method": "hard", "overlap_lr": 0}):
+        monkeypatch.delenv("FSR_NO_PHASES", raising=False)
+        got, n, _ = eng.run_raster(depth, dem, **kw)
+        monkeypatch.setenv("FSR_TAIL_PARTS", "1")
+        one, _, _ = eng.run_raster(depth, dem, **kw)
+        monkeypatch.delenv("FSR_TAIL_PARTS")
+        monkeypatch.setenv("FSR_NO_PHASES", "1")
+        want, n_ref, _ = eng.run_raster(depth, dem, **kw)
+        assert n == n_ref and n >= 3 * 26
+        assert np.array_equal(got, want) and np.array_equal(one, want)
+    eng.close()
+
+
 def test_run_raster_input_assertions(engine):
     depth, dem = synth_raster(1024, 1024, seed=3)
     with pytest.raises(AssertionError, match="depth shape"):
