@@ -700,7 +700,7 @@ def test_fused_and_unfused_high_resolution_paths_agree(h1_model_fp, monkeypatch)
     pair.close()
 
 
-@pytest.mark.parametrize("h,w,world", [(2048, 1024, 2), (4096, 1024, 3)])
+@pytest.mark.parametrize("h,w,world", [(2048, 1024, 2), (4096, 1024, 3), (1664, 6400, 2)])  # 17 window columns: the last band runs in column parts
 def test_band_host_pipeline_is_bit_identical_to_single_pass(tc_engine, h, w, world):
     """Host-buffer band path (pipelined copies, deferred blend of the rows shared with the previous rank)."""
     from floodsr_b200 import _lib

@@ -22,6 +22,22 @@ def test_geotiff_round_trip(tmp_path, compression):
     assert tuple(r["geo_tags"][TAG_GEOKEYS]) == UTM32
 
 
+@pytest.mark.parametrize("compression", ["tiff_lzw", "raw", "tiff_adobe_deflate"])
+def test_written_geotiff_is_read_by_an_independent_decoder(tmp_path, compression):
+    """The files the run writes are what GDAL-side consumers read: OpenCV's bundled libtiff (not Pillow, which wrote them)
+    must decode the same float32 samples.  A TIFF without georeferencing tags (what OpenCV writes) is refused on the way in."""
+    cv2 = pytest.importorskip("cv2")
+    arr = (np.random.default_rng(1).random((257, 333)) * 10 - 3).astype(np.float32)
+    t = bounds_to_transform(0.0, 0.0, 333.0, 257.0, 333, 257)
+    fp = write_geotiff(tmp_path / "w.tif", arr, t, nodata=-9999.0, geo_tags={TAG_GEOKEYS: UTM32}, compression=compression)
+    seen = cv2.imread(str(fp), cv2.IMREAD_UNCHANGED)
+    assert seen is not None and seen.dtype == np.float32 and np.array_equal(seen, arr)
+    fp2 = tmp_path / "cv.tif"
+    assert cv2.imwrite(str(fp2), arr)
+    with pytest.raises(AssertionError, match="no georeferencing"):
+        read_geotiff(fp2)
+
+
 @pytest.mark.parametrize("nodata", [float("nan"), float("inf"), float("-inf"), -3.4028234663852886e38, 0.5])
 def test_non_integer_and_non_finite_nodata_round_trips(tmp_path, nodata):
     """GDAL_NODATA "nan" is what float DEMs usually carry: writing the prediction next to such a DEM must not fail."""

@@ -56,6 +56,29 @@ def test_oracle_reproduces_a_plane_when_upsampling():
     assert np.abs(out[2:-2, 2:-2] - want[2:-2, 2:-2]).max() < 1e-3
 
 
+@pytest.mark.parametrize("s_shape,d_shape", [((225, 240), (240, 256)), ((64, 48), (128, 96)), ((32, 32), (512, 512)), ((50, 70), (50, 70))])
+def test_oracle_up_sampling_agrees_with_opencv_and_scipy(s_shape, d_shape):
+    """Independent cross-check of the 4-sample path (the reference's 15x -> 16x DEM case and the 16x way back are up-sampling).
+
+    GDAL is absent, but two unrelated libraries implement the same published convention -- sample at pixel centres, weights
+    1 - |distance|, at the raster edge only the pixels that exist count (weight renormalisation == border replication for
+    two taps): `cv2.resize(INTER_LINEAR)` and `scipy.ndimage.map_coordinates(order=1, mode="nearest")`.  This pins the
+    restatement's geometry and edge rule; the down-sampling kernel (widened triangle filter) stays GDAL-specific and
+    unpinned."""
+    cv2 = pytest.importorskip("cv2")
+    ndi = pytest.importorskip("scipy.ndimage")
+    src = _grid(*s_shape, seed=11)
+    ts, td = _transforms(s_shape, d_shape)
+    got = oracle_resample(src, ts, d_shape, td)
+    want_cv = cv2.resize(src, (d_shape[1], d_shape[0]), interpolation=cv2.INTER_LINEAR)
+    sy = (np.arange(d_shape[0]) + 0.5) * s_shape[0] / d_shape[0] - 0.5
+    sx = (np.arange(d_shape[1]) + 0.5) * s_shape[1] / d_shape[1] - 0.5
+    want_sp = ndi.map_coordinates(src.astype(np.float64), np.meshgrid(sy, sx, indexing="ij"), order=1, mode="nearest")
+    scale = float(np.abs(src).max())
+    assert np.abs(got - want_sp).max() <= 2e-7 * scale      # float64 accumulation on both sides, one float32 rounding
+    assert np.abs(got - want_cv).max() <= 2e-5 * scale      # OpenCV interpolates with 11-bit fixed-point weights for some sizes
+
+
 def test_oracle_nodata_and_outside():
     s_shape, d_shape = (60, 75), (64, 80)
     ts, td = _transforms(s_shape, d_shape)
