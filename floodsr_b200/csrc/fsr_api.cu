@@ -119,7 +119,7 @@ Engine::~Engine() {
   for (auto& b : tbuf_) b.release();
   for (auto& b : simt_buf_) b.release();
   for (DeviceBuf* b : {&d_weights_, &d_flags_, &d_headmid_, &d_dem_norm_, &d_depth_norm_, &d_pred_norm_, &d_dem_lr_, &d_tiles, &d_stats,
-                       &d_in_depth, &d_in_dem, &d_out, &d_tmp_a, &d_tmp_b})
+                       &d_in_depth, &d_in_dem, &d_out, &d_tmp_a, &d_tmp_b, &d_norm_ws})
     b->release();
   win.release();
   d_big2_.release();
@@ -297,8 +297,9 @@ void Engine::run_tiles_from_grid(const float* d_depth, const float* d_dem, const
     const bool lazy = p.normalize_inputs && !no_lazy_dem_ && lazy_dem_ok();
     {
       ProfScope scope(prof, PROF_PROLOGUE, s);
+      d_norm_ws.ensure(tile_normalize_ws_bytes(cap_tiles_));
       launch_tile_normalize(d_dem, d_depth, grid, tile_base + c0, n, T, TL, hdr_.scale, p, lazy ? nullptr : d_dem_norm_.as<float>(),
-                            d_depth_norm_.as<float>(), d_stats_out, d_dem_lr_.as<float>(), d_flags(), s);
+                            d_depth_norm_.as<float>(), d_stats_out, d_dem_lr_.as<float>(), d_flags(), s, d_norm_ws.p);
     }
     dem_lr_pre_ = p.normalize_inputs ? d_dem_lr_.as<float>() : nullptr;
     dem_src_ = DemSource{};
@@ -330,8 +331,9 @@ void Engine::group_lr(const float* d_depth, const float* d_dem, const TileGrid& 
   const bool lazy = p.normalize_inputs && !no_lazy_dem_ && lazy_dem_ok();  // see run_tiles_from_grid
   {
     ProfScope scope(prof, PROF_PROLOGUE, s);
+    d_norm_ws.ensure(tile_normalize_ws_bytes(cap_tiles_));
     launch_tile_normalize(d_dem, d_depth, grid, 0, n, hdr_.hr_tile, hdr_.lr_tile, hdr_.scale, p, lazy ? nullptr : d_dem_norm_.as<float>(),
-                          d_depth_norm_.as<float>(), d_stats, d_dem_lr_.as<float>(), d_flags(), s);
+                          d_depth_norm_.as<float>(), d_stats, d_dem_lr_.as<float>(), d_flags(), s, d_norm_ws.p);
   }
   dem_lr_pre_ = p.normalize_inputs ? d_dem_lr_.as<float>() : nullptr;
   dem_src_ = DemSource{};
@@ -1206,8 +1208,9 @@ int fsr_stage_normalize(fsr_engine* eng, const float* depth_lr, const float* dem
   e.d_tmp_a.ensure(org.size() * sizeof(int));
   FSR_CUDA(cudaMemcpyAsync(e.d_tmp_a.p, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   TileGrid grid{e.d_tmp_a.as<int2>(), n_tiles * T, T, n_tiles * TL, TL};
+  e.d_norm_ws.ensure(tile_normalize_ws_bytes(n_tiles));
   launch_tile_normalize(e.d_in_dem.as<float>(), e.d_in_depth.as<float>(), grid, 0, n_tiles, T, TL, e.scale(), *params,
-                        e.d_out.as<float>(), e.d_tmp_b.as<float>(), e.d_stats.as<float>(), nullptr, e.d_flags(), s);
+                        e.d_out.as<float>(), e.d_tmp_b.as<float>(), e.d_stats.as<float>(), nullptr, e.d_flags(), s, e.d_norm_ws.p);
   if (out_depth_norm) FSR_CUDA(cudaMemcpyAsync(out_depth_norm, e.d_tmp_b.p, lr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (out_dem_norm) FSR_CUDA(cudaMemcpyAsync(out_dem_norm, e.d_out.p, hr_px * n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (out_stats) FSR_CUDA(cudaMemcpyAsync(out_stats, e.d_stats.p, (size_t)n_tiles * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -85,7 +85,8 @@ struct DeviceBuf {
 // kernel launchers (k_prologue.cu, k_fp32.cu, k_blend.cu)
 void launch_tile_normalize(const float* d_dem, const float* d_depth, const TileGrid& grid, int tile_base, int n_tiles,
                            int T, int TL, int scale, const fsr_tile_params& p, float* d_dem_norm, float* d_depth_norm,
-                           float* d_stats, float* d_dem_lr, unsigned* d_flags, cudaStream_t stream);
+                           float* d_stats, float* d_dem_lr, unsigned* d_flags, cudaStream_t stream, void* d_ws = nullptr);
+size_t tile_normalize_ws_bytes(int n_tiles);  // workspace of the three-kernel path (d_ws; nullptr = one CTA per tile)
 void launch_conv_fp32(const float* src0, int C0, const float* src1, int C1, const float* w, const float* bias,
                       const float* res, float* dst, int n_img, int H, int W, int k, int cout, int act, float alpha,
                       cudaStream_t s);
@@ -186,6 +187,7 @@ class Engine {
   DeviceBuf d_stats;      // [n_tiles][3]
   DeviceBuf d_in_depth, d_in_dem, d_out;  // staging for the host-buffer entry points
   DeviceBuf d_tmp_a, d_tmp_b;
+  DeviceBuf d_norm_ws;    // workspace of the three-kernel normalisation (tile_normalize_ws_bytes)
   // fsr_run_raster pipeline: compute / H2D / D2H streams and the two hand-over buffers for rows shared by
   // consecutive bands
   cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;

@@ -51,8 +51,16 @@ def _hex(stats):
 # ---------------------------------------------------------------------------------------------------------
 
 
+@pytest.fixture(params=["0", "1"], ids=["one-cta", "three-kernel"])
+def norm_path(request, monkeypatch):
+    """Both normalisation paths of launch_tile_normalize (k_prologue.cu): one CTA per tile (large batches) and the
+    scan / select / apply kernels (batches of <= 2 tiles per SM).  FSR_NORM_SPLIT forces one or the other."""
+    monkeypatch.setenv("FSR_NORM_SPLIT", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("case", mg.tile_cases(), ids=lambda c: c[0])
-def test_normalize_stage_matches_reference_golden_bit_exact(engine, golden, case):
+def test_normalize_stage_matches_reference_golden_bit_exact(engine, golden, case, norm_path):
     from oracle import preprocessing_np as pp
 
     meta, arrays = golden
@@ -66,7 +74,7 @@ def test_normalize_stage_matches_reference_golden_bit_exact(engine, golden, case
     assert np.abs(got["depth_norm"][0] - want_depth).max() <= 2.4e-7  # log1pf vs libm: <= 2 ulp at 1.0
 
 
-def test_normalize_stage_random_tiles_vs_oracle(engine):
+def test_normalize_stage_random_tiles_vs_oracle(engine, norm_path):
     from oracle import preprocessing_np as pp
 
     rng = np.random.default_rng(5)
@@ -84,7 +92,7 @@ def test_normalize_stage_random_tiles_vs_oracle(engine):
             assert np.array_equal(got["dem_norm"][i], want), (pct, i)
 
 
-def test_normalize_stage_ref_stats_and_errors(engine):
+def test_normalize_stage_ref_stats_and_errors(engine, norm_path):
     from oracle import preprocessing_np as pp
 
     depth, dem = synth_tile(9)
@@ -552,6 +560,25 @@ def test_last_band_in_column_parts_is_bit_identical(h1_model_fp, monkeypatch, pr
         assert n == n_ref and n >= 3 * 26
         assert np.array_equal(got, want) and np.array_equal(one, want)
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_normalisation_paths_feed_the_network_the_same_bits(h1_model_fp, monkeypatch, precision):
+    """The pooled low-resolution DEM (and in the 16-bit mode the normalised tiles) come out of either normalisation path with
+    the same summation order: predictions are bit-identical."""
+    from floodsr_b200.engine import EngineB200
+
+    depth = np.stack([synth_depth(32, 32, seed=40 + i) for i in range(5)])
+    dem = np.stack([synth_dem(512, 512, seed=40 + i) for i in range(5)])
+    dem[3, :, 200:] = 0.0
+    eng = EngineB200(h1_model_fp, precision=precision)
+    monkeypatch.setenv("FSR_NORM_SPLIT", "0")
+    a = eng.run_tiles(depth, dem)
+    monkeypatch.setenv("FSR_NORM_SPLIT", "1")
+    b = eng.run_tiles(depth, dem)
+    eng.close()
+    assert a["dem_stats_used"] == b["dem_stats_used"]
+    assert np.array_equal(a["prediction_m"], b["prediction_m"])
 
 
 def test_run_raster_input_assertions(engine):
