@@ -576,13 +576,23 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
 static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1, bool single_rows = false) {
   const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T, H = e.win.H;
   // band size: the engine's target, but at least ~4 bands per call so that small rasters still overlap copies and kernels;
-  // single_rows (two-phase pipeline, where the batched layers run per GROUP of bands): one window row per band
+  // single_rows: the two-phase pipeline, where the batched layers run per GROUP of bands and a band only has to feed the fused kernel
   const int total = (ty1 - ty0) * nx;
   const int target = std::min(e.band_tiles_target(), std::max(64, ceil_div(total, 4)));
-  const int rows_per_band = single_rows ? 1 : std::max(1, ceil_div(target, nx));
   std::vector<int> band_ty{ty0};  // band b covers window rows [band_ty[b], band_ty[b + 1])
-  if (ty1 - ty0 >= 3 && rows_per_band > 1) band_ty.push_back(ty0 + 1);
-  while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
+  if (single_rows) {
+    // one window row per band, or as many rows as make ~64 windows on narrow rasters (a launch of the fused kernel wants
+    // >= 148 x a few rows); what follows the last kernel is exposed, so the last band's worth of rows goes in bands of ~16
+    // windows (one row on wide rasters, where the last one is cut into column parts as well)
+    const int rows_per_band = std::max(1, ceil_div(64, nx)), tail_rows = std::max(1, ceil_div(16, nx));
+    int y = ty0;
+    while (ty1 - y >= 2 * rows_per_band) band_ty.push_back(y += rows_per_band);
+    while (ty1 - y > tail_rows) band_ty.push_back(y += tail_rows);
+  } else {
+    const int rows_per_band = std::max(1, ceil_div(target, nx));
+    if (ty1 - ty0 >= 3 && rows_per_band > 1) band_ty.push_back(ty0 + 1);
+    while (band_ty.back() + rows_per_band < ty1) band_ty.push_back(band_ty.back() + rows_per_band);
+  }
   band_ty.push_back(ty1);
   for (size_t b = 0; b + 1 < band_ty.size();) {
     const bool receives = band_ty[b] > 0;
@@ -629,7 +639,12 @@ static std::vector<int> group_plan(const Engine& e, const std::vector<int>& band
 
 // the two-phase pipeline applies when the fused tensor-core kernels run the high-resolution layers and no band exceeds a chunk
 static bool use_phases(const Engine& e, const fsr_tile_params& p, const std::vector<int>& band_ty) {
-  if (getenv("FSR_NO_PHASES") || !e.phases_ok() || !p.normalize_inputs) return false;  // (read per call: the tests switch it)
+  // FSR_PHASES=0 / 1 overrides the default (read per call: the tests switch it).  Default: the compute-bound fp32 mode only --
+  // in the 16-bit mode a window row is computed faster than PCIe delivers it, what matters there is an early first band, and
+  // the band pipeline measured equal (4096 x 32768) or faster (8192 x 8192: 8.6 vs 9.3 ms; 256 tiles: 8.2 vs 9.6 ms)
+  const char* force = getenv("FSR_PHASES");
+  const bool want = force ? atoi(force) != 0 : e.compute_bound();
+  if (!want || !e.phases_ok() || !p.normalize_inputs) return false;
   for (size_t b = 0; b + 1 < band_ty.size(); ++b)
     if ((long long)(band_ty[b + 1] - band_ty[b]) * (long long)e.win.xs.size() > e.chunk_tiles()) return false;
   return true;

@@ -170,6 +170,7 @@ class Engine {
   // band of the same group is still computing.  Per-window results do not depend on how windows are batched.
   bool phases_ok() const { return precision_ != FSR_PREC_FP32_SIMT && fused_ct_ >= 0 && pooled_op_ != fused_ct_ && pooled_op_ != fused_hd_; }
   int chunk_tiles() const { return chunk_tiles_; }
+  bool compute_bound() const { return precision_ == FSR_PREC_FP32; }  // kernels, not PCIe copies, bound the host-buffer pipelines
   void group_lr(const float* d_depth, const float* d_dem, const TileGrid& grid, int n_tiles, const fsr_tile_params& p, float* d_stats,
                 cudaStream_t s);
   void group_hr(int sub0, int m, float* d_pred_m, const fsr_tile_params& p, cudaStream_t s);

@@ -517,25 +517,26 @@ def test_large_overlaps_three_window_rows_per_coordinate(h1_model_fp, oracle_eng
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_two_phase_pipeline_is_bit_identical_to_band_pipeline(h1_model_fp, monkeypatch, precision):
     """fsr_run_raster runs the low-resolution layers per GROUP of window rows and the fused high-resolution kernel per window
-    row (two-phase pipeline); FSR_NO_PHASES=1 runs every band in one piece.  Per-window results do not depend on how the
+    row (two-phase pipeline, the fp32 mode's default; FSR_PHASES=1 / 0 forces it on / off); otherwise every band runs in one piece.  Per-window results do not depend on how the
     windows are batched, so the two mosaics, and the mosaics of other group sizes, are the same bits (7 window rows: groups
     of 1, 2, 4 rows by default)."""
     from floodsr_b200.engine import EngineB200
 
     depth, dem = synth_raster(2816, 1280, seed=77)
     eng = EngineB200(h1_model_fp, precision=precision)
+    monkeypatch.setenv("FSR_PHASES", "1")
     got, n, summary = eng.run_raster(depth, dem)
-    monkeypatch.setenv("FSR_NO_PHASES", "1")
+    monkeypatch.setenv("FSR_PHASES", "0")
     want, n_ref, summary_ref = eng.run_raster(depth, dem)
-    monkeypatch.delenv("FSR_NO_PHASES")
     eng.close()
     assert n == n_ref and n >= 21 and summary == summary_ref
     assert np.array_equal(got, want)
     monkeypatch.setenv("FSR_GROUP_TILES", "8")  # two window rows per group at most
     small = EngineB200(h1_model_fp, precision=precision)
     monkeypatch.delenv("FSR_GROUP_TILES")
+    monkeypatch.setenv("FSR_PHASES", "1")
     got_small, _, _ = small.run_raster(depth, dem, window_method="hard", overlap_lr=0)
-    monkeypatch.setenv("FSR_NO_PHASES", "1")
+    monkeypatch.setenv("FSR_PHASES", "0")
     want_small, _, _ = small.run_raster(depth, dem, window_method="hard", overlap_lr=0)
     small.close()
     assert np.array_equal(got_small, want_small)
@@ -550,12 +551,12 @@ def test_last_band_in_column_parts_is_bit_identical(h1_model_fp, monkeypatch, pr
     depth, dem = synth_raster(1280, 13184, seed=5)
     eng = EngineB200(h1_model_fp, precision=precision)
     for kw in ({}, {"window_method": "hard", "overlap_lr": 0}):
-        monkeypatch.delenv("FSR_NO_PHASES", raising=False)
+        monkeypatch.setenv("FSR_PHASES", "1")
         got, n, _ = eng.run_raster(depth, dem, **kw)
         monkeypatch.setenv("FSR_TAIL_PARTS", "1")
         one, _, _ = eng.run_raster(depth, dem, **kw)
         monkeypatch.delenv("FSR_TAIL_PARTS")
-        monkeypatch.setenv("FSR_NO_PHASES", "1")
+        monkeypatch.setenv("FSR_PHASES", "0")
         want, n_ref, _ = eng.run_raster(depth, dem, **kw)
         assert n == n_ref and n >= 3 * 26
         assert np.array_equal(got, want) and np.array_equal(one, want)
@@ -728,13 +729,17 @@ def test_fused_and_unfused_high_resolution_paths_agree(h1_model_fp, monkeypatch)
 
 
 @pytest.mark.parametrize("h,w,world", [(2048, 1024, 2), (4096, 1024, 3), (1664, 6400, 2)])  # 17 window columns: the last band runs in column parts
-def test_band_host_pipeline_is_bit_identical_to_single_pass(tc_engine, h, w, world):
-    """Host-buffer band path (pipelined copies, deferred blend of the rows shared with the previous rank)."""
+@pytest.mark.parametrize("phases", ["0", "1"])
+def test_band_host_pipeline_is_bit_identical_to_single_pass(tc_engine, h, w, world, phases, monkeypatch):
+    """Host-buffer band path (pipelined copies, deferred blend of the rows shared with the previous rank), as the band
+    pipeline and as the two-phase pipeline (the fp32 mode's default)."""
     from floodsr_b200 import _lib
     from floodsr_b200.dist import CudaBandExecutor, plan_bands
 
     depth, dem = synth_raster(h, w, seed=h + 1)
+    monkeypatch.setenv("FSR_PHASES", "0")
     want, _, _ = tc_engine.run_raster(depth, dem)
+    monkeypatch.setenv("FSR_PHASES", phases)
     plans, ys, xs = plan_bands(h, w, 512, "feather", 128, world)
     ex = CudaBandExecutor(tc_engine, h, w, "feather", 128)
     got = np.empty_like(want)
