@@ -573,14 +573,14 @@ static void band_run(Engine& e, const float* d_depth, const float* d_dem, int ba
 // kernels efficient, small enough to overlap copies; the first band is a single window row so that the pipeline fills fast.
 // A band must own at least the rows it receives partial sums for (three or more window rows covering one coordinate:
 // overlap >= tile / 2 or a forced trailing window close to its predecessor): such a band takes over the following window rows.
-static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1, bool single_rows = false) {
+static std::vector<int> sub_band_plan(const Engine& e, int ty0, int ty1, bool two_phase = false) {
   const int ny = (int)e.win.ys.size(), nx = (int)e.win.xs.size(), T = e.win.T, H = e.win.H;
   // band size: the engine's target, but at least ~4 bands per call so that small rasters still overlap copies and kernels;
-  // single_rows: the two-phase pipeline, where the batched layers run per GROUP of bands and a band only has to feed the fused kernel
+  // two_phase: the two-phase pipeline, where the batched layers run per GROUP of bands and a band only has to feed the fused kernel
   const int total = (ty1 - ty0) * nx;
   const int target = std::min(e.band_tiles_target(), std::max(64, ceil_div(total, 4)));
   std::vector<int> band_ty{ty0};  // band b covers window rows [band_ty[b], band_ty[b + 1])
-  if (single_rows) {
+  if (two_phase) {
     // one window row per band, or as many rows as make ~64 windows on narrow rasters (a launch of the fused kernel wants
     // >= 148 x a few rows); what follows the last kernel is exposed, so the last band's worth of rows goes in bands of ~16
     // windows (one row on wide rasters, where the last one is cut into column parts as well)
