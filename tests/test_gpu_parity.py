@@ -805,6 +805,25 @@ def test_bench_size_raster_is_periodic_for_periodic_inputs(fp16_engine):
     assert np.array_equal(out, again)
 
 
+def test_bench_size_raster_fp32_mode_two_phase_pipeline(engine, monkeypatch):
+    """The same workload in the fp32 mode, whose default is the two-phase pipeline (groups of 1, 2, 4, 4 window rows, last band
+    in 4 column parts at 85 window columns): periodic like the inputs, and the same bits as the band pipeline."""
+    h, w, period = 4096, 32768, 384
+    depth_p, dem_p = synth_raster(h, period, seed=22)
+    reps = -(-w // period)
+    dem = np.ascontiguousarray(np.tile(dem_p, (1, reps))[:, :w])
+    depth = np.ascontiguousarray(np.tile(depth_p, (1, reps))[:, : w // 16])
+    monkeypatch.delenv("FSR_PHASES", raising=False)
+    out, n_tiles, _ = engine.run_raster(depth, dem)
+    assert n_tiles == 935 and out.shape == (h, w) and np.isfinite(out).all() and out.min() >= 0.0 and out.max() <= 5.0
+    ref = out[:, 2 * period: 3 * period]
+    for k in (3, 21, 22, 42, 43, 63, 64, 82):   # includes the window columns either side of the column-part cuts
+        assert np.array_equal(out[:, k * period: (k + 1) * period], ref), k
+    monkeypatch.setenv("FSR_PHASES", "0")
+    bands, _, _ = engine.run_raster(depth, dem)
+    assert np.array_equal(out, bands)
+
+
 def test_batch_256_equals_single_tiles_in_tensor_core_mode(fp16_engine):
     """BASELINE config 3 (256 independent tiles): a tile's result does not depend on the batch it travels in."""
     from floodsr_b200.synth import synth_tile
