@@ -377,6 +377,15 @@ def roofline_of(args, res, peaks, n_tiles_mine):
     fp = REPO / "profiles" / ("fused_hr_x3_kernel_ncu.json" if precision == "fp32" else "fused_hr_kernel_ncu.json")
     if fp.exists():
         ncu = json.loads(fp.read_text())
+    # tensor-pipe activity of every tensor-core kernel of the step (committed ncu captures of this command, see profiles/README.md)
+    by_kernel = {}
+    if ncu and ncu.get("tensor_pipe_pct") is not None:
+        by_kernel["fused_hr_x3_kernel" if precision == "fp32" else "fused_hr_kernel"] = {"tensor_pipe_pct": ncu["tensor_pipe_pct"]}
+    fp_conv = REPO / "profiles" / "r2" / f"conv_kernels_{precision}_ncu.json"
+    if fp_conv.exists():
+        for k, v in json.loads(fp_conv.read_text()).get("kernels", {}).items():
+            by_kernel[k] = {"tensor_pipe_pct": v["tensor_pipe_pct_time_weighted"], "range": [v["tensor_pipe_pct_min"], v["tensor_pipe_pct_max"]],
+                            "launches_per_step": v["launches"]}
     traffic = None
     if ncu:
         try:
@@ -401,6 +410,7 @@ def roofline_of(args, res, peaks, n_tiles_mine):
         "traffic": traffic,
         "tensor_pipe_pct": (ncu or {}).get("tensor_pipe_pct"),
         "tensor_pipe_source": (ncu or {}).get("tensor_pipe_metric"),
+        "tensor_pipe_pct_by_kernel": by_kernel or None,
         "note": "timed inside the step with CUDA events around each launch; FLOPs = transposed convolution + head of the tiles in the launch",
     }
 
