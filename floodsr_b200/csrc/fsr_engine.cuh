@@ -131,6 +131,8 @@ struct TcOp {
   DeviceBuf packbuf;       // CP8 staging tensor for convs fed by 1-channel fp32 rasters
   bool pack_small = false;
   bool rows = false;       // runs the persistent row-box conv kernel
+  bool folded = false;     // UPSAMPLE: 2x nearest upsampling folded into the convolution that reads it; the op does not run
+  int up_src = -1;         // CONV: src0 is read through a folded upsampling from this (smaller) tensor
   int kc = 0, C0 = 0, C1 = 0;
   float out_scale = 1.0f;  // split mode: inverse of the power-of-two factor carried by the packed weights
   std::vector<float> h_wdem, h_bias, h_w2;  // head epilogue constants (passed as kernel parameters)
@@ -224,6 +226,7 @@ class Engine {
   void tc_run_fused(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s, int sub0 = 0);
   int group_n_ = 0;                     // windows of the group whose low-resolution result is resident (group_lr)
   void run_hr_simt(int n, float* d_pred_m, float max_depth, float denom, cudaStream_t s);
+  bool force_folded_ = false;           // debug_read_tensor: run a folded upsampling op after all
   bool hr_simt_ = false;                // the high-resolution layers run on the fp32 FMA kernels (shapes the tcgen05 kernels do not cover)
   int parts_ = 1;                       // 2: split fp16 (hi, lo) tensors and weights, three MMAs per product (FSR_PREC_FP32)
   int fused_ct_ = -1, fused_hd_ = -1;   // plan ops run by the fused high-resolution kernel, or -1

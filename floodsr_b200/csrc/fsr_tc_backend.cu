@@ -20,7 +20,7 @@ int conv_tc_bn(int cout, int parts, int hh_steps);
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
-                    int parts, float out_scale, int cpad_out, unsigned* flags, cudaStream_t s);
+                    int parts, float out_scale, int cpad_out, unsigned* flags, cudaStream_t s, int up0 = 0);
 bool conv_rows_ok(int H, int W, int ksz, int cout, int C0, int C1, int kc, int parts);
 void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                          const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
@@ -155,6 +155,29 @@ void Engine::tc_prepare(const float* w) {
     }
     hr_simt_ = !ok;
   }
+  // 2x nearest upsampling folded into the convolution that consumes it (conv_tc_kernel, ConvTcParams::up0): image-major
+  // levels only (maps of <= 64 pixels), the upsampled tensor must have no other reader.  FSR_NO_FOLD_UP=1 keeps the two ops.
+  if (!getenv("FSR_NO_FOLD_UP"))
+    for (size_t ui = 0; ui < ops_.size(); ++ui) {
+      const fsr_op& up = ops_[ui];
+      if (up.kind != FSR_OP_UPSAMPLE || up.mode != FSR_UP_NEAREST || up.k != 2 || op_hr_[ui]) continue;
+      if (!tc_fmt_[up.src0] || !tc_im_[up.src0] || !tc_im_[up.dst] || up.dst == hdr_.out_tensor) continue;
+      int reader = -1, n_readers = 0;
+      for (size_t oi = 0; oi < ops_.size(); ++oi) {
+        const fsr_op& o = ops_[oi];
+        if (o.src0 == up.dst || o.src1 == up.dst || o.res == up.dst) {
+          ++n_readers;
+          reader = (int)oi;
+        }
+      }
+      if (n_readers != 1) continue;
+      const fsr_op& cv = ops_[reader];
+      if (cv.kind != FSR_OP_CONV || cv.k != 3 || cv.src0 != up.dst || cv.src1 < 0 || cv.src1 == up.dst || cv.res == up.dst ||
+          !tc_fmt_[cv.src1] || !tc_im_[cv.dst] || op_hr_[reader])
+        continue;
+      tc_ops_[ui].folded = true;
+      tc_ops_[reader].up_src = up.src0;
+    }
   for (size_t oi = 0; oi < ops_.size(); ++oi) {
     const fsr_op& op = ops_[oi];
     TcOp& t = tc_ops_[oi];
@@ -200,12 +223,14 @@ void Engine::tc_prepare(const float* w) {
       t.C1 = C1;
       const int taps = op.k * op.k;
       const int s0 = (C0 / 8) / kc, s1 = C1 ? (C1 / 8) / kc : 0;
-      const int BN = t.rows ? op.cout : conv_tc_bn(op.cout, parts_, taps * (s0 + s1) * (kc / 2));
+      const bool fold = t.up_src >= 0;
+      FSR_REQUIRE(!(fold && (t.rows || t.pack_small)), "folded upsampling is conv_tc_kernel's (image-major levels)");
+      const int BN = t.rows ? op.cout : conv_tc_bn(op.cout, parts_, (fold ? 4 * s0 + 9 * s1 : taps * (s0 + s1)) * (kc / 2));
       const int n_tiles = ceil_div(op.cout, BN);
       const int real_c0 = t.pack_small ? tensors_[op.src0].c + (op.src1 >= 0 ? tensors_[op.src1].c : 0) : tensors_[op.src0].c;
       const int real_c1 = t.pack_small ? 0 : (op.src1 >= 0 ? tensors_[op.src1].c : 0);
       const int cin_real = real_c0 + real_c1;
-      std::vector<uint16_t> pk((size_t)parts_ * n_tiles * taps * (s0 + s1) * kc * BN * 8, 0);
+      std::vector<uint16_t> pk((size_t)parts_ * n_tiles * (fold ? 16 * s0 + 9 * s1 : taps * (s0 + s1)) * kc * BN * 8, 0);
       const float* wt = w + op.w_off;  // [tap][cin_real][cout]
       const float wscale = parts_ == 2 ? split_weight_scale(wt, (size_t)taps * cin_real * op.cout) : 1.0f;
       t.out_scale = 1.0f / wscale;
@@ -214,7 +239,50 @@ void Engine::tc_prepare(const float* w) {
       const size_t slice = (size_t)kc * BN * 8;
       const size_t part_stride = t.rows ? (size_t)taps * (s0 + s1) * slice : slice;
       const size_t stage_stride = t.rows ? slice : (size_t)parts_ * slice;
-      for (int nt_i = 0; nt_i < n_tiles; ++nt_i)
+      // folded upsampling: src0's taps that share a pixel of the smaller map are summed per output parity.  Along one axis an
+      // even output coordinate reaches source offsets {-1: tap -1; 0: taps 0, +1}, an odd one {0: taps -1, 0; +1: tap +1}.
+      if (fold) {
+        const size_t fold_elems = (size_t)n_tiles * 16 * s0 * stage_stride;
+        auto taps_of = [](int parity, int a, int (&d)[2]) {  // taps (0 .. 2) that land on source pixel a (0 / 1) of the pair
+          int n = 0;
+          for (int k = 0; k < 3; ++k)
+            if ((parity == 0 ? (k == 0 ? 0 : 1) : (k == 2 ? 1 : 0)) == a) d[n++] = k;
+          return n;
+        };
+        for (int nt_i = 0; nt_i < n_tiles; ++nt_i)
+          for (int par = 0; par < 4; ++par)
+            for (int q = 0; q < 4; ++q) {
+              int dys[2], dxs[2];
+              const int ny_t = taps_of(par >> 1, q >> 1, dys), nx_t = taps_of(par & 1, q & 1, dxs);
+              for (int st = 0; st < s0; ++st)
+                for (int j = 0; j < kc; ++j)
+                  for (int n = 0; n < BN; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                      const int co = nt_i * BN + n, ci = (st * kc + j) * 8 + e;
+                      if (ci >= real_c0 || co >= op.cout) continue;
+                      double v = 0.0;
+                      for (int a = 0; a < ny_t; ++a)
+                        for (int b = 0; b < nx_t; ++b) v += wt[((size_t)(dys[a] * 3 + dxs[b]) * cin_real + ci) * op.cout + co];
+                      const size_t pos = ((((size_t)nt_i * 4 + par) * 4 + q) * s0 + st) * stage_stride + ((size_t)j * BN + n) * 8 + e;
+                      if (parts_ == 2) split_weight((float)v * wscale, pk[pos], pk[pos + part_stride]);
+                      else pk[pos] = f2bf((float)v);
+                    }
+            }
+        for (int nt_i = 0; nt_i < n_tiles; ++nt_i)
+          for (int tap = 0; tap < taps; ++tap)
+            for (int st = 0; st < s1; ++st)
+              for (int j = 0; j < kc; ++j)
+                for (int n = 0; n < BN; ++n)
+                  for (int e = 0; e < 8; ++e) {
+                    const int co = nt_i * BN + n, c = (st * kc + j) * 8 + e;
+                    if (c >= real_c1 || co >= op.cout) continue;
+                    const size_t pos = fold_elems + (((size_t)nt_i * taps + tap) * s1 + st) * stage_stride + ((size_t)j * BN + n) * 8 + e;
+                    const float v = wt[((size_t)tap * cin_real + real_c0 + c) * op.cout + co];
+                    if (parts_ == 2) split_weight(v * wscale, pk[pos], pk[pos + part_stride]);
+                    else pk[pos] = f2bf(v);
+                  }
+      }
+      for (int nt_i = 0; nt_i < (fold ? 0 : n_tiles); ++nt_i)
         for (int tap = 0; tap < taps; ++tap)
           for (int st = 0; st < s0 + s1; ++st)
             for (int j = 0; j < kc; ++j)
@@ -541,8 +609,9 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
           s0 = pb;
           pl0 = plane;
         } else {
-          s0 = cp8(op.src0);
-          pl0 = tc_plane(op.src0);
+          const int t0 = tc.up_src >= 0 ? tc.up_src : op.src0;  // folded upsampling: the level below feeds the convolution directly
+          s0 = cp8(t0);
+          pl0 = tc_plane(t0);
           if (op.src1 >= 0) {
             s1 = cp8(op.src1);
             pl1 = tc_plane(op.src1);
@@ -554,7 +623,7 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
         else
           launch_conv_tc(s0, tc.C0, pl0, s1, tc.C1, pl1, tc.wpack.as<__nv_bfloat16>(), tc.kc, wp(op.b_off), cp8(op.res), cp8(op.dst),
                          tc_plane(op.dst), n, td.h, td.w, op.k, op.cout, op.act, op.alpha, half, tc_im_[op.dst], parts, tc.out_scale,
-                         tc_cpad_[op.dst], d_flags(), s);
+                         tc_cpad_[op.dst], d_flags(), s, tc.up_src >= 0 ? 1 : 0);
         break;
       }
       case FSR_OP_POOL:
@@ -565,6 +634,7 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
           launch_pool_fp32(f32(op.src0), f32(op.dst), n, ts.h, ts.w, ts.c, op.k, op.mode, op.aux, s);
         break;
       case FSR_OP_UPSAMPLE:
+        if (tc.folded && !force_folded_) break;  // its only reader takes the level below (TcOp::up_src)
         launch_upsample_cp8(cp8(op.src0), cp8(op.dst), tc_cpad_[op.src0] / 8, n, ts.h, ts.w, op.k, tc_plane(op.src0), tc_plane(op.dst),
                             tc_im_[op.src0], tc_im_[op.dst], op.mode, half, parts, s);
         break;
@@ -605,6 +675,13 @@ void Engine::tc_run_one(int i, int n, int sub_start, float* d_pred_m, float max_
 
 void Engine::debug_read_tensor(int tid, int n_tiles, float* d_out, cudaStream_t s) {
   FSR_REQUIRE(tid >= 0 && tid < (int)tensors_.size() && tbase_[tid], "tensor is not materialised");
+  if (precision_ != FSR_PREC_FP32_SIMT)
+    for (size_t oi = 0; oi < ops_.size(); ++oi)
+      if (tc_ops_[oi].folded && ops_[oi].dst == tid) {  // never written by the forward pass: produce it now for the reader
+        force_folded_ = true;
+        tc_run_one((int)oi, n_tiles, 0, nullptr, 1.f, 1.f, s, n_sms_);
+        force_folded_ = false;
+      }
   const auto& t = tensors_[tid];
   const long long n_pix = (long long)n_tiles * t.h * t.w;
   if (precision_ != FSR_PREC_FP32_SIMT && tc_fmt_[tid]) {

@@ -91,6 +91,10 @@ struct ConvTcParams {
   int im;                  // 1: image-major tensors ("IM8" [C/8][H*W][N][8], maps of <= 64 pixels): an M tile is 128 images at
                            // one output pixel, each tap is ONE contiguous 2 KB run per channel chunk, out-of-range taps are skipped
   int ncap;                // images per pixel plane of IM8 tensors (allocation capacity)
+  int up0;                 // im only: src0 is the level BELOW (H/2 x W/2) and the graph's 2x nearest upsampling is folded into this
+                           // convolution: the 3 x 3 taps of an output pixel hit 2 x 2 pixels of the smaller map, so the taps that
+                           // share a source pixel are summed on the host (weights per output parity, `wpack` layout below) and
+                           // src0 costs 4 instead of 9 K steps per channel stage; the upsampled tensor is never written
   int parts;               // 1: plain 16-bit operands; 2: split fp16 (hi, lo) operands, three MMAs per product (tc_common.cuh)
   int nacc;                // parts == 2: the K steps of the hi*hi products rotate over `nacc` TMEM accumulators and the small
                            // hi*lo / lo*hi products go to one more, all summed in fp32 registers by the epilogue: the tensor core
@@ -98,7 +102,8 @@ struct ConvTcParams {
   float out_scale;         // parts == 2: the packed weights carry a power-of-two factor, undone here
   long long lo_off;        // parts == 2: elements between the hi and the lo tensor of out / res
   long long plane;         // pixels per CP8 plane of the output/residual tensors (N_capacity * H * W)
-  const __nv_bfloat16* wpack;  // [n_tile][tap][stage][part][kc][BN][8]
+  const __nv_bfloat16* wpack;  // [n_tile][tap][stage][part][kc][BN][8]; up0: [n_tile][parity 2 x 2][source pixel 2 x 2][s0 stages][..]
+                               // for src0, followed by [n_tile][tap][s1 stages][..] for src1
   const float* bias;           // [cout] or nullptr
   const __nv_bfloat16* res;    // CP8 residual or nullptr
   __nv_bfloat16* out;          // CP8 output
@@ -146,7 +151,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   };
   int n_taps_ok = 0;
   for (int tap = 0; tap < taps; ++tap) n_taps_ok += tap_ok(tap) ? 1 : 0;
-  const int n_iters_cta = n_taps_ok * stages_per_tap;
+  // up0: pixel (a, b) of the 2 x 2 block of the smaller map that the taps of output pixel (ty, tx) reach; -1 = outside the map
+  // (exactly when all taps that map to it fall into the zero padding)
+  auto fold_pix = [&](int q) {
+    const int r = (ty >> 1) + (q >> 1) - (1 - (ty & 1)), c = (tx >> 1) + (q & 1) - (1 - (tx & 1));
+    return (r >= 0 && r < (p.H >> 1) && c >= 0 && c < (p.W >> 1)) ? r * (p.W >> 1) + c : -1;
+  };
+  int n_fold_ok = 0;
+  if (p.up0)
+    for (int q = 0; q < 4; ++q) n_fold_ok += fold_pix(q) >= 0 ? 1 : 0;
+  const int n_iters_cta = p.up0 ? n_fold_ok * p.s0 + n_taps_ok * p.s1 : n_taps_ok * stages_per_tap;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -176,10 +190,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       const int pad = p.ksz / 2;
       int it = 0;
+      const size_t stage_elems = (size_t)PARTS * p.kc * BN * 8;
+      if (p.up0) {
+        // src0 through the folded upsampling: one K run per reachable pixel of the smaller map, weights of this pixel's parity
+        const int par = (ty & 1) * 2 + (tx & 1);
+        for (int q = 0; q < 4; ++q) {
+          const int pix = fold_pix(q);
+          if (pix < 0) continue;
+          for (int st = 0; st < p.s0; ++st, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], PAIR * a_bytes + b_bytes);
+            for (int h = 0; h < PAIR; ++h)
+              tma_load_5d(smem_a + s * a_stage + h * kABytesMax, &tmA0, &full[s], (tn0 + h) * 256, pix, st * p.kc, 0, 0);
+            bulk_load_1d(smem_b + s * kBBytesMax, p.wpack + ((((size_t)n_tile * 4 + par) * 4 + q) * p.s0 + st) * stage_elems, b_bytes, &full[s]);
+          }
+        }
+      }
+      const __nv_bfloat16* wtaps = p.up0 ? p.wpack + (size_t)gridDim.y * 16 * p.s0 * stage_elems : p.wpack;
+      const int st_begin = p.up0 ? p.s0 : 0, st_per_tap = p.up0 ? p.s1 : stages_per_tap;
       for (int tap = 0; tap < taps; ++tap) {
         if (!tap_ok(tap)) continue;
         const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
-        for (int st = 0; st < stages_per_tap; ++st, ++it) {
+        for (int st = st_begin; st < stages_per_tap; ++st, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -192,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (p.im) tma_load_5d(dst, tm, &full[s], (tn0 + h) * 256, (ty + dy) * p.W + tx + dx, chunk0, 0, 0);
             else tma_load_5d(dst, tm, &full[s], 2 * (tx * p.bw + dx), ty * p.bh + dy, (tn0 + h) * p.bn, chunk0, 0);
           }
-          const __nv_bfloat16* wsrc = p.wpack + ((size_t)(n_tile * taps + tap) * stages_per_tap + st) * ((size_t)PARTS * p.kc * BN * 8);
+          const __nv_bfloat16* wsrc = wtaps + ((size_t)(n_tile * taps + tap) * st_per_tap + (st - st_begin)) * stage_elems;
           bulk_load_1d(smem_b + s * kBBytesMax, wsrc, b_bytes, &full[s]);
         }
       }
@@ -1035,8 +1069,10 @@ int conv_tc_bn(int cout, int parts, int hh_steps) {
 void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const __nv_bfloat16* src1, int C1, long long plane1,
                     const __nv_bfloat16* wpack, int kc, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* dst,
                     long long plane_out, int n_img, int H, int W, int ksz, int cout, int act, float alpha, int half, int im,
-                    int parts, float out_scale, int cpad_out, unsigned* flags, cudaStream_t s) {
+                    int parts, float out_scale, int cpad_out, unsigned* flags, cudaStream_t s, int up0) {
   ConvTcParams p{};
+  FSR_REQUIRE(!up0 || (im && ksz == 3 && src1 && H % 2 == 0 && W % 2 == 0), "folded upsampling needs an image-major 3 x 3 layer with a second source");
+  p.up0 = up0;
   p.flags = flags;
   p.half = half;
   p.parts = parts;
@@ -1067,12 +1103,13 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
   p.res = res;
   p.out = dst;
   const int tiles_n = ceil_div(n_img, p.bn);
-  CUtensorMap m0 = im ? make_im8_tensor_map(src0, plane0 / ((long long)H * W), H * W, C0 / 8, kc, parts)
+  CUtensorMap m0 = up0 ? make_im8_tensor_map(src0, plane0 / ((long long)(H / 2) * (W / 2)), (H / 2) * (W / 2), C0 / 8, kc, parts)
+                   : im ? make_im8_tensor_map(src0, plane0 / ((long long)H * W), H * W, C0 / 8, kc, parts)
                       : make_cp8_wide_tensor_map(src0, W, H, n_img, C0 / 8, plane0, p.bw, p.bh, p.bn, kc, parts);
   CUtensorMap m1 = !src1 ? m0
                    : im  ? make_im8_tensor_map(src1, plane1 / ((long long)H * W), H * W, C1 / 8, kc, parts)
                          : make_cp8_wide_tensor_map(src1, W, H, n_img, C1 / 8, plane1, p.bw, p.bh, p.bn, kc, parts);
-  const int n_iters = ksz * ksz * (p.s0 + p.s1);
+  const int n_iters = up0 ? 4 * p.s0 + 9 * p.s1 : ksz * ksz * (p.s0 + p.s1);
   // split mode: 1, 3 or 7 accumulators for the hi*hi products (+ 1 for the small ones; a power-of-two TMEM allocation), so
   // that one accumulation chain stays short: the tensor core truncates on every addition into an accumulator
   const int hh_steps = n_iters * (kc / 2);
