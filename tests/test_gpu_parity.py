@@ -582,6 +582,30 @@ def test_normalisation_paths_feed_the_network_the_same_bits(h1_model_fp, monkeyp
     assert np.array_equal(a["prediction_m"], b["prediction_m"])
 
 
+@pytest.mark.parametrize("precision,tol_m", [("fp32", 5e-5), ("fp16", 5e-3)])
+def test_folded_upsampling_agrees_with_the_two_op_path(h1_model_fp, oracle_engine, monkeypatch, precision, tol_m):
+    """The 2x nearest upsampling in front of the image-major decoder convolutions is folded into them (weights of the taps that
+    share a source pixel summed per output parity); FSR_NO_FOLD_UP=1 runs upsampling and convolution as two ops.  Both stay
+    within the mode's tolerance of the oracle and close to one another (sum of products vs product with the summed weight)."""
+    from floodsr_b200.engine import EngineB200
+
+    depth = np.stack([synth_depth(32, 32, seed=60 + i) for i in range(3)])
+    dem = np.stack([synth_dem(512, 512, seed=60 + i) for i in range(3)])
+    folded = EngineB200(h1_model_fp, precision=precision)
+    monkeypatch.setenv("FSR_NO_FOLD_UP", "1")
+    two_op = EngineB200(h1_model_fp, precision=precision)
+    monkeypatch.delenv("FSR_NO_FOLD_UP")
+    a = folded.run_tiles(depth, dem)["prediction_m"]
+    b = two_op.run_tiles(depth, dem)["prediction_m"]
+    assert folded.launch_count() < two_op.launch_count()  # two upsampling launches fewer per pass
+    folded.close()
+    two_op.close()
+    want = np.stack([oracle_engine.run_tile(depth[i], dem[i])["prediction_m"] for i in range(3)])
+    bound = FP32_TOL_M if precision == "fp32" else 1e-2
+    assert np.abs(a - want).max() <= bound and np.abs(b - want).max() <= bound
+    assert np.abs(a - b).max() <= tol_m
+
+
 def test_run_raster_input_assertions(engine):
     depth, dem = synth_raster(1024, 1024, seed=3)
     with pytest.raises(AssertionError, match="depth shape"):
