@@ -1197,8 +1197,24 @@ void launch_conv_rows_tc(const __nv_bfloat16* src0, int C0, long long plane0, co
   ConvRowsParams p{};
   p.flags = flags;
   p.parts = parts;
-  p.sets = parts == 2 ? 2 : kRowsEpiSets;  // split mode: 2 buffers x (nacc + 1) accumulators x cout columns = 512
-  p.nacc = parts == 2 ? (cout == 64 ? 3 : 7) : 1;
+  // split mode: the same chain policy as conv_tc_kernel (the fewest of 1 / 3 / 7 accumulators that keeps every accumulation
+  // chain <= 48 MMAs: these layers have 9 - 18 K steps per output, one chain), then as many accumulator buffers / epilogue
+  // sets as TMEM holds: sets x (nacc + 1) x cout columns, a power of two.  (Measured: 2 buffers x 8 accumulators 3.33 ms for
+  // the LR convolutions of a step, 4 x 4 3.22 ms, 4 x 2 3.16 ms.)  FSR_ROWS_CFG="nacc,sets" overrides (A/B).
+  p.sets = kRowsEpiSets;
+  p.nacc = 1;
+  if (parts == 2) {
+    const int hh_steps = 9 * ((C0 + C1) / 16);
+    p.nacc = split_nacc(hh_steps, 512 / cout - 1);
+    while (p.sets > 1 && p.sets * (p.nacc + 1) * cout > 512) p.sets /= 2;
+    if (const char* e = getenv("FSR_ROWS_CFG")) {
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && (a == 1 || a == 3 || a == 7) && (b == 1 || b == 2 || b == 4) && b * (a + 1) * cout <= 512) {
+        p.nacc = a;
+        p.sets = b;
+      }
+    }
+  }
   p.out_scale = parts == 2 ? out_scale : 1.0f;
   p.lo_off = parts == 2 ? (long long)(cout / 8) * plane_out * 8 : 0;
   p.H = H; p.W = W; p.N = n_img;
