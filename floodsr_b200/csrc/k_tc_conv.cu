@@ -1129,7 +1129,7 @@ void launch_conv_tc(const __nv_bfloat16* src0, int C0, long long plane0, const _
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
       FSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     }
-    p.stages = conv_stages<128>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2);
+    p.stages = conv_stages<128>(kc * parts, n_iters, (long long)grid.x * grid.y, p.pair, parts == 2 && p.pair * 128 * (p.nacc + 1) > 256);
     if (parts == 2) launch_pdl(conv_tc_kernel<128, 1, 2>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
     else if (p.pair == 2) launch_pdl(conv_tc_kernel<128, 2, 1>, grid, kConvThreads<2>, conv_smem_bytes<128>(kc * parts, p.stages, 2), s, m0, m1, p);
     else launch_pdl(conv_tc_kernel<128, 1, 1>, grid, kConvThreads<1>, conv_smem_bytes<128>(kc * parts, p.stages, 1), s, m0, m1, p);
