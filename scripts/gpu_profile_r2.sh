@@ -1,5 +1,6 @@
 #!/bin/bash
 # Round-2 profiling pass on the B200 box (run under gpurun): launch lists + full captures of the tensor-core kernels.
+# LAUNCHES = kernel launches per bench step (37 in both modes since the folded upsampling; 39 before).
 # Every ncu command follows a plain run of the same command line that exited 0 (B200_PROFILING.md).  gpurun_out/ may hold at
 # most 64 MiB: the 27-kernel convolution captures are reduced to their raw-page CSV on the box.
 mkdir -p gpurun_out
@@ -7,7 +8,7 @@ TM="sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_ten
 for prec in ${PRECS:-fp32 fp16}; do
   B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-modes --precision $prec"
   $B > gpurun_out/plain_$prec.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -s 117 -c 39 --csv --log-file gpurun_out/launches_r2_$prec.csv $B > gpurun_out/ncu_launch_$prec.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * ${LAUNCHES:-37})) -c ${LAUNCHES:-37} --csv --log-file gpurun_out/launches_r2_$prec.csv $B > gpurun_out/ncu_launch_$prec.log 2>&1
   echo "launch list $prec rc=$?"
   $B > gpurun_out/plain_$prec.log 2>&1 &&
   ncu --set full --metrics $TM --clock-control none --import-source on -k regex:fused_hr -s 3 -c 1 -f -o gpurun_out/prof_fused_$prec $B > gpurun_out/ncu_fused_$prec.log 2>&1
